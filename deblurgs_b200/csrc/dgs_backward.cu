@@ -1,0 +1,594 @@
+// Backward kernels of the batched blurry-view rasterizer (sm_100a).
+//
+// Reference behaviour restated here (taekkii/deblurgs, submodules/diff-gaussian-rasterization):
+//   tile blending backward    cuda_rasterizer/backward.cu:463-640
+//   cov2D backward            cuda_rasterizer/backward.cu:145-295
+//   preprocess / SH / cov3D   cuda_rasterizer/backward.cu:20-140, 299-362, 367-460
+// including its gradient conventions ("quirks"): mean2D gradients
+// are w.r.t. NDC; the view-matrix gradient flows through the view-space mean t and the
+// depth only; the projection-matrix gradient carries the extra 0.5*W / 0.5*H factor and one
+// shared last-row term; quaternion and scale gradients ignore normalisation / scale_modifier.
+//
+// Design differences (B200-first): the reference issues 10 global float atomics per
+// contributing (pixel, Gaussian) pair.  Here a warp first reduces the 10 components over its
+// 32 pixels with a 12-shuffle halving exchange (each step trades half of the remaining
+// components with the partner lane), which leaves the 10 totals in 10 distinct lanes; those
+// lanes then issue ONE warp-wide RED into a 48-B AoS gradient record.  The per-Gaussian
+// stage is one kernel (the reference has two) whose threads loop over the F sub-frames and
+// keep the Gaussian's parameter gradients in registers, writing them once per blurry view;
+// view/projection-matrix gradients are warp-reduced the same way and accumulated in fp64.
+#include "dgs_internal.cuh"
+
+namespace dgs {
+
+#define FULL_MASK 0xffffffffu
+
+// Halving exchange: reduce N per-lane values over the 32 lanes of a warp.  After the call,
+// out holds the total of component `warp_reduce_owner_component(lane)` (or garbage when that
+// is < 0).  Costs ceil(N/2)+ceil(N/4)+... shuffles instead of 5*N.
+template <int N>
+struct HalvingReduce {
+    // one exchange step over distance DIST on an array of CNT live values
+    template <int CNT, int DIST>
+    static __device__ __forceinline__ void step(float (&v)[N], unsigned lane)
+    {
+        constexpr int KEEP = (CNT + 1) / 2;  // lower half keeps [0,KEEP), upper keeps [KEEP,CNT)
+        const bool up = (lane & DIST) != 0;
+#pragma unroll
+        for (int i = 0; i < KEEP; i++) {
+            const float hi = (i + KEEP < CNT) ? v[i + KEEP] : 0.0f;
+            const float send = up ? v[i] : hi;
+            const float keep = up ? hi : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL_MASK, send, DIST);
+        }
+    }
+    static __device__ __forceinline__ float run(float (&v)[N], unsigned lane)
+    {
+        constexpr int C1 = N, C2 = (C1 + 1) / 2, C3 = (C2 + 1) / 2, C4 = (C3 + 1) / 2, C5 = (C4 + 1) / 2;
+        if (C1 > 1) step<C1, 16>(v, lane); else v[0] += __shfl_xor_sync(FULL_MASK, v[0], 16);
+        if (C2 > 1) step<C2, 8>(v, lane); else v[0] += __shfl_xor_sync(FULL_MASK, v[0], 8);
+        if (C3 > 1) step<C3, 4>(v, lane); else v[0] += __shfl_xor_sync(FULL_MASK, v[0], 4);
+        if (C4 > 1) step<C4, 2>(v, lane); else v[0] += __shfl_xor_sync(FULL_MASK, v[0], 2);
+        if (C5 > 1) step<C5, 1>(v, lane); else v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
+        return v[0];
+    }
+    // which component's total does `lane` hold after run()?  (-1: none / padding)
+    static __device__ __forceinline__ int owner(unsigned lane)
+    {
+        int base = 0, live = N, cnt = N;  // cnt follows the compile-time sequence used by run()
+#pragma unroll
+        for (int dist = 16; dist >= 1; dist >>= 1) {
+            if (cnt > 1) {
+                const int keep = (cnt + 1) / 2;
+                if (lane & dist) { base += keep; live -= keep; } else { live = min(live, keep); }
+                if (live <= 0) return -1;   // this lane ended up on zero padding
+                cnt = keep;
+            } else if (lane & dist) {
+                return -1;  // duplicate holder; only the lane with the bit clear reports
+            }
+        }
+        return base;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// tile blending, backward.  grid = (tiles_x, tiles_y, F), 256 threads = 16x16 pixels;
+// a warp covers a 16x2 pixel strip.  grad = AoS float[N][12]:
+//   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7,8,9 dcolor | 10,11 unused
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __restrict__ grad)
+{
+    const FwdParams& f = p.f;
+    const int s = blockIdx.z;
+    const int tile = blockIdx.y * f.tiles_x + blockIdx.x;
+    const int tid = threadIdx.y * DGS_TILE_X + threadIdx.x;
+    const unsigned lane = tid & 31;
+    const unsigned pixx = blockIdx.x * DGS_TILE_X + threadIdx.x;
+    const unsigned pixy = blockIdx.y * DGS_TILE_Y + threadIdx.y;
+    const bool inside = pixx < (unsigned)f.W && pixy < (unsigned)f.H;
+    const size_t HW = (size_t)f.H * f.W;
+    const size_t pix_id = (size_t)f.W * pixy + pixx;
+    const float pixfx = (float)pixx, pixfy = (float)pixy;
+
+    const uint2 range = p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile];
+
+    __shared__ int s_id[DGS_TILE_PIX];
+    __shared__ float2 s_xy[DGS_TILE_PIX];
+    __shared__ float4 s_con[DGS_TILE_PIX];
+    __shared__ float4 s_rgbd[DGS_TILE_PIX];
+
+    const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
+    const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
+    const float4* __restrict__ geo2 = f.geo2 + (size_t)s * f.P;
+    float* __restrict__ grad_s = grad + (size_t)s * f.P * 12;
+
+    const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)p.n_contrib[(size_t)s * HW + pix_id] : 0;
+
+    // Nothing behind the deepest contributor of the tile can receive gradient: restrict the
+    // replay to the first `tile_max` list entries (identical results, less staging).
+    __shared__ int s_max;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+        if (lane == 0) atomicMax(&s_max, m);
+    }
+    __syncthreads();
+    const int list_len = min((int)(range.y - range.x), s_max);
+    int warp_max = last_contributor;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) warp_max = max(warp_max, __shfl_xor_sync(FULL_MASK, warp_max, d));
+
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpixd = 0.f;
+    if (inside) {
+        if (p.dL_dpix) {
+            const float* d = p.dL_dpix + (size_t)s * 3 * HW;
+            dpix0 = d[pix_id]; dpix1 = d[HW + pix_id]; dpix2 = d[2 * HW + pix_id];
+        }
+        if (p.dL_dpixdepth) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
+    }
+    float bg_dot_dpixel = 0.f;
+    bg_dot_dpixel += f.background[0] * dpix0;
+    bg_dot_dpixel += f.background[1] * dpix1;
+    bg_dot_dpixel += f.background[2] * dpix2;
+    bg_dot_dpixel += f.z_far * dpixd;
+
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;
+    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_depth = 0.f;
+    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+
+    const int rounds = (list_len + DGS_TILE_PIX - 1) / DGS_TILE_PIX;
+    int todo = list_len;
+    int contributor = list_len;  // index (within the list) of the entry being replayed, +1
+    const int my_comp = HalvingReduce<10>::owner(lane);
+
+    for (int i = 0; i < rounds; i++, todo -= DGS_TILE_PIX) {
+        __syncthreads();
+        const int progress = i * DGS_TILE_PIX + tid;
+        if (progress < list_len) {
+            const uint32_t id = p.point_list[range.x + list_len - progress - 1];
+            const float4 a = geo0[id];
+            const float4 c = geo2[id];
+            s_id[tid] = (int)id;
+            s_xy[tid] = make_float2(a.x, a.y);
+            s_con[tid] = geo1[id];
+            s_rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
+        }
+        __syncthreads();
+        const int batch = min(DGS_TILE_PIX, todo);
+        for (int j = 0; j < batch; j++) {
+            contributor--;
+            if (contributor >= warp_max) continue;  // warp-uniform
+            float v[10];
+            bool contrib = false;
+            float4 con_o;
+            float dx, dy, G, alpha;
+            if (inside && contributor < last_contributor) {
+                const float2 xy = s_xy[j];
+                dx = xy.x - pixfx; dy = xy.y - pixfy;
+                con_o = s_con[j];
+                const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+                if (power <= 0.0f) {
+                    G = expf(power);
+                    alpha = min(0.99f, con_o.w * G);
+                    contrib = alpha >= 1.0f / 255.0f;
+                }
+            }
+            if (!__any_sync(FULL_MASK, contrib)) continue;
+            if (contrib) {
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                const float4 cd = s_rgbd[j];
+                float dL_dalpha = 0.0f;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = cd.x;
+                dL_dalpha += (cd.x - acc0) * dpix0;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = cd.y;
+                dL_dalpha += (cd.y - acc1) * dpix1;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cd.z;
+                dL_dalpha += (cd.z - acc2) * dpix2;
+                accd = last_alpha * last_depth + (1.f - last_alpha) * accd; last_depth = cd.w;
+                dL_dalpha += (cd.w - accd) * dpixd;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                const float dL_dG = con_o.w * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+                v[6] = dchannel_dcolor * dpixd;
+                v[7] = dchannel_dcolor * dpix0;
+                v[8] = dchannel_dcolor * dpix1;
+                v[9] = dchannel_dcolor * dpix2;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 10; k++) v[k] = 0.f;
+            }
+            const float total = HalvingReduce<10>::run(v, lane);
+            if (my_comp >= 0) atomicAdd(grad_s + (size_t)s_id[j] * 12 + my_comp, total);
+        }
+    }
+}
+
+void launch_render_bwd(const BwdParams& p, cudaStream_t st)
+{
+    const FwdParams& f = p.f;
+    if (f.F == 0 || f.W == 0 || f.H == 0) return;
+    dim3 grid(f.tiles_x, f.tiles_y, f.F), block(DGS_TILE_X, DGS_TILE_Y);
+    k_render_bwd<<<grid, block, 0, st>>>(p, reinterpret_cast<float*>(p.g0));
+}
+
+// ---------------------------------------------------------------------------------------
+// per-Gaussian backward: cov2D, projection, SH and cov3D stages for all F sub-frames.
+// ---------------------------------------------------------------------------------------
+#define NPOSE 21
+// pose component order: view {0,1,2,4,5,6,8,9,10,12,13,14} -> 0..11, proj {0,1,4,5,8,9,12,13}
+// -> 12..19, proj last-row term (entries 3,7,11,15) -> 20
+__device__ static const int kPoseSlot[NPOSE] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14,
+                                                16, 17, 20, 21, 24, 25, 28, 29, 19};
+
+template <int DEG>
+__global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const float* __restrict__ grad)
+{
+    const FwdParams& f = p.f;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const bool live = g < f.P;
+    const int gi = live ? g : 0;
+
+    const float3 mean = {f.means3D[3 * gi], f.means3D[3 * gi + 1], f.means3D[3 * gi + 2]};
+    float cov3D[6];
+    float3 scale = {0.f, 0.f, 0.f};
+    float4 q = {0.f, 0.f, 0.f, 0.f};
+    if (f.cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) cov3D[i] = f.cov3D_precomp[6 * (size_t)gi + i];
+    } else {
+        q = reinterpret_cast<const float4*>(f.rotations)[gi];
+        scale = {f.scales[3 * gi], f.scales[3 * gi + 1], f.scales[3 * gi + 2]};
+        cov3d_from_scale_rot(scale.x, scale.y, scale.z, f.scale_modifier, q, cov3D);
+    }
+
+    constexpr int NC = DEG >= 0 ? (DEG + 1) * (DEG + 1) : 1;
+    float sh[NC][3];
+    float dsh[NC][3];
+#pragma unroll
+    for (int k = 0; k < NC; k++) { dsh[k][0] = dsh[k][1] = dsh[k][2] = 0.f; sh[k][0] = sh[k][1] = sh[k][2] = 0.f; }
+    if (DEG >= 0) {
+        const float* src = f.shs + (size_t)gi * f.M * 3;
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            sh[k][0] = __ldg(src + 3 * k); sh[k][1] = __ldg(src + 3 * k + 1); sh[k][2] = __ldg(src + 3 * k + 2);
+        }
+    }
+
+    float3 dmean = {0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dopac = 0.f;
+    float3 dcolor_acc = {0.f, 0.f, 0.f};
+    const int my_comp = HalvingReduce<NPOSE>::owner(lane);
+    const int my_slot = my_comp >= 0 ? kPoseSlot[my_comp] : -1;
+
+    for (int s = 0; s < f.F; s++) {
+        const size_t n = (size_t)s * f.P + gi;
+        const bool vis = live && f.radii[n] > 0;
+        if (p.dL_dmeans2D != nullptr && live) {
+            float gx = 0.f, gy = 0.f;
+            if (vis) { gx = grad[n * 12]; gy = grad[n * 12 + 1]; }
+            p.dL_dmeans2D[n * 3] = gx; p.dL_dmeans2D[n * 3 + 1] = gy; p.dL_dmeans2D[n * 3 + 2] = 0.f;
+        }
+        if (!__any_sync(FULL_MASK, vis)) continue;
+        float pv[NPOSE];
+#pragma unroll
+        for (int k = 0; k < NPOSE; k++) pv[k] = 0.f;
+        if (vis) {
+            const float* __restrict__ V = f.view + 16 * s;
+            const float* __restrict__ PM = f.proj + 16 * s;
+            const float4 ga = reinterpret_cast<const float4*>(grad)[n * 3];
+            const float4 gb = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
+            const float4 gc = reinterpret_cast<const float4*>(grad)[n * 3 + 2];
+            const float dm2x = ga.x, dm2y = ga.y;
+            const float3 dconic = {ga.z, ga.w, gb.x};
+            dopac += gb.y;
+            const float ddepth = gb.z;
+            float3 dcol = {gb.w, gc.x, gc.y};
+
+            // ---- cov2D / EWA backward (reference backward.cu:145-295)
+            const Ewa e = ewa_project(mean, f.focal_x, f.focal_y, f.tan_fovx, f.tan_fovy, cov3D, V);
+            const float limx = 1.3f * f.tan_fovx, limy = 1.3f * f.tan_fovy;
+            const float x_grad_mul = (e.txtz < -limx || e.txtz > limx) ? 0.f : 1.f;
+            const float y_grad_mul = (e.tytz < -limy || e.tytz > limy) ? 0.f : 1.f;
+            const float a = e.a, b = e.b, c = e.c;
+            const float denom = a * c - b * b;
+            float dL_da = 0, dL_db = 0, dL_dc = 0;
+            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+            const Mat3& T = e.T;
+            if (denom2inv != 0) {
+                dL_da = denom2inv * (-c * c * dconic.x + 2 * b * c * dconic.y + (denom - a * c) * dconic.z);
+                dL_dc = denom2inv * (-a * a * dconic.z + 2 * a * b * dconic.y + (denom - a * c) * dconic.x);
+                dL_db = denom2inv * 2 * (b * c * dconic.x - (denom + 2 * b * b) * dconic.y + a * b * dconic.z);
+                dcov[0] += (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+                dcov[3] += (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+                dcov[5] += (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+                dcov[1] += 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+                dcov[2] += 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+                dcov[4] += 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+            }
+            // Vrk (symmetric)
+            const float V00 = cov3D[0], V01 = cov3D[1], V02 = cov3D[2], V11 = cov3D[3], V12 = cov3D[4], V22 = cov3D[5];
+            const float r0x = T.m[0][0] * V00 + T.m[0][1] * V01 + T.m[0][2] * V02;
+            const float r0y = T.m[0][0] * V01 + T.m[0][1] * V11 + T.m[0][2] * V12;
+            const float r0z = T.m[0][0] * V02 + T.m[0][1] * V12 + T.m[0][2] * V22;
+            const float r1x = T.m[1][0] * V00 + T.m[1][1] * V01 + T.m[1][2] * V02;
+            const float r1y = T.m[1][0] * V01 + T.m[1][1] * V11 + T.m[1][2] * V12;
+            const float r1z = T.m[1][0] * V02 + T.m[1][1] * V12 + T.m[1][2] * V22;
+            const float dL_dT00 = 2 * r0x * dL_da + r1x * dL_db;
+            const float dL_dT01 = 2 * r0y * dL_da + r1y * dL_db;
+            const float dL_dT02 = 2 * r0z * dL_da + r1z * dL_db;
+            const float dL_dT10 = 2 * r1x * dL_dc + r0x * dL_db;
+            const float dL_dT11 = 2 * r1y * dL_dc + r0y * dL_db;
+            const float dL_dT12 = 2 * r1z * dL_dc + r0z * dL_db;
+            const Mat3& W = e.W;
+            const float dL_dJ00 = W.m[0][0] * dL_dT00 + W.m[0][1] * dL_dT01 + W.m[0][2] * dL_dT02;
+            const float dL_dJ02 = W.m[2][0] * dL_dT00 + W.m[2][1] * dL_dT01 + W.m[2][2] * dL_dT02;
+            const float dL_dJ11 = W.m[1][0] * dL_dT10 + W.m[1][1] * dL_dT11 + W.m[1][2] * dL_dT12;
+            const float dL_dJ12 = W.m[2][0] * dL_dT10 + W.m[2][1] * dL_dT11 + W.m[2][2] * dL_dT12;
+            const float tz = 1.f / e.t.z;
+            const float tz2 = tz * tz;
+            const float tz3 = tz2 * tz;
+            const float hx = f.focal_x, hy = f.focal_y;
+            const float dL_dtx = x_grad_mul * -hx * tz2 * dL_dJ02;
+            const float dL_dty = y_grad_mul * -hy * tz2 * dL_dJ12;
+            const float dL_dtz = -hx * tz2 * dL_dJ00 - hy * tz2 * dL_dJ11 + (2 * hx * e.t.x) * tz3 * dL_dJ02 + (2 * hy * e.t.y) * tz3 * dL_dJ12;
+            // dL/dmean through t (V^T applied to the 3-vector)
+            float3 dm;
+            dm.x = V[0] * dL_dtx + V[1] * dL_dty + V[2] * dL_dtz;
+            dm.y = V[4] * dL_dtx + V[5] * dL_dty + V[6] * dL_dtz;
+            dm.z = V[8] * dL_dtx + V[9] * dL_dty + V[10] * dL_dtz;
+            // view-matrix gradient through t only (reference quirk, backward.cu:279-293)
+            pv[0] = dL_dtx * mean.x; pv[1] = dL_dty * mean.x; pv[2] = dL_dtz * mean.x;
+            pv[3] = dL_dtx * mean.y; pv[4] = dL_dty * mean.y; pv[5] = dL_dtz * mean.y;
+            pv[6] = dL_dtx * mean.z; pv[7] = dL_dty * mean.z; pv[8] = dL_dtz * mean.z;
+            pv[9] = dL_dtx; pv[10] = dL_dty; pv[11] = dL_dtz;
+
+            // ---- projection of the mean (reference backward.cu:396-457)
+            const float4 m_hom = xform_point_4x4(mean, PM);
+            const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+            const float mul1 = (PM[0] * mean.x + PM[4] * mean.y + PM[8] * mean.z + PM[12]) * m_w * m_w;
+            const float mul2 = (PM[1] * mean.x + PM[5] * mean.y + PM[9] * mean.z + PM[13]) * m_w * m_w;
+            dm.x += (PM[0] * m_w - PM[3] * mul1) * dm2x + (PM[1] * m_w - PM[3] * mul2) * dm2y + ddepth * V[2];
+            dm.y += (PM[4] * m_w - PM[7] * mul1) * dm2x + (PM[5] * m_w - PM[7] * mul2) * dm2y + ddepth * V[6];
+            dm.z += (PM[8] * m_w - PM[11] * mul1) * dm2x + (PM[9] * m_w - PM[11] * mul2) * dm2y + ddepth * V[10];
+
+            const float lastcol = (m_hom.x * f.W * dm2x + m_hom.y * f.H * dm2y) * m_w * m_w;
+            const float wx = 0.5f * dm2x * f.W * m_w, wy = 0.5f * dm2y * f.H * m_w;
+            pv[12] = wx * mean.x; pv[13] = wy * mean.x;
+            pv[14] = wx * mean.y; pv[15] = wy * mean.y;
+            pv[16] = wx * mean.z; pv[17] = wy * mean.z;
+            pv[18] = wx;          pv[19] = wy;
+            pv[20] = -0.5f * lastcol;
+            // depth part of the view-matrix gradient (backward.cu:454-457)
+            pv[2] += ddepth * mean.x; pv[5] += ddepth * mean.y; pv[8] += ddepth * mean.z; pv[11] += ddepth;
+
+            // ---- colour: SH backward (reference backward.cu:20-140) or precomputed colour
+            if (DEG >= 0) {
+                const float3 cam = {f.campos[3 * s], f.campos[3 * s + 1], f.campos[3 * s + 2]};
+                const float3 dir_orig = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
+                const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+                const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+                const unsigned mask = __float_as_uint(f.geo2[n].w);
+                float dRGB[3] = {dcol.x, dcol.y, dcol.z};
+                if (f.use_sigmoid) {
+                    // recompute the pre-activation colour
+                    float pre[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) pre[ch] = kSH0 * sh[0][ch];
+                    if (DEG > 0) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++)
+                            pre[ch] = pre[ch] - kSH1 * y * sh[1][ch] + kSH1 * z * sh[2][ch] - kSH1 * x * sh[3][ch];
+                        if (DEG > 1) {
+                            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                            for (int ch = 0; ch < 3; ch++)
+                                pre[ch] = pre[ch] + kSH2[0] * xy * sh[4][ch] + kSH2[1] * yz * sh[5][ch] +
+                                          kSH2[2] * (2.0f * zz - xx - yy) * sh[6][ch] + kSH2[3] * xz * sh[7][ch] +
+                                          kSH2[4] * (xx - yy) * sh[8][ch];
+                            if (DEG > 2) {
+#pragma unroll
+                                for (int ch = 0; ch < 3; ch++)
+                                    pre[ch] = pre[ch] + kSH3[0] * y * (3.0f * xx - yy) * sh[9][ch] +
+                                              kSH3[1] * xy * z * sh[10][ch] +
+                                              kSH3[2] * y * (4.0f * zz - xx - yy) * sh[11][ch] +
+                                              kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12][ch] +
+                                              kSH3[4] * x * (4.0f * zz - xx - yy) * sh[13][ch] +
+                                              kSH3[5] * z * (xx - yy) * sh[14][ch] +
+                                              kSH3[6] * x * (xx - 3.0f * yy) * sh[15][ch];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const float sg = 1.0f / (1.0f + expf(-pre[ch]));
+                        dRGB[ch] *= sg * (1.0f - sg);
+                    }
+                } else {
+                    dRGB[0] *= (mask & 1u) ? 1.f : 0.f;
+                    dRGB[1] *= (mask & 2u) ? 1.f : 0.f;
+                    dRGB[2] *= (mask & 4u) ? 1.f : 0.f;
+                }
+                float dRGBdx[3] = {0.f, 0.f, 0.f}, dRGBdy[3] = {0.f, 0.f, 0.f}, dRGBdz[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) dsh[0][ch] += kSH0 * dRGB[ch];
+                if (DEG > 0) {
+                    const float b1 = -kSH1 * y, b2 = kSH1 * z, b3 = -kSH1 * x;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        dsh[1][ch] += b1 * dRGB[ch]; dsh[2][ch] += b2 * dRGB[ch]; dsh[3][ch] += b3 * dRGB[ch];
+                        dRGBdx[ch] = -kSH1 * sh[3][ch]; dRGBdy[ch] = -kSH1 * sh[1][ch]; dRGBdz[ch] = kSH1 * sh[2][ch];
+                    }
+                    if (DEG > 1) {
+                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                        const float b4 = kSH2[0] * xy, b5 = kSH2[1] * yz, b6 = kSH2[2] * (2.f * zz - xx - yy);
+                        const float b7 = kSH2[3] * xz, b8 = kSH2[4] * (xx - yy);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) {
+                            dsh[4][ch] += b4 * dRGB[ch]; dsh[5][ch] += b5 * dRGB[ch]; dsh[6][ch] += b6 * dRGB[ch];
+                            dsh[7][ch] += b7 * dRGB[ch]; dsh[8][ch] += b8 * dRGB[ch];
+                            dRGBdx[ch] += kSH2[0] * y * sh[4][ch] + kSH2[2] * 2.f * -x * sh[6][ch] + kSH2[3] * z * sh[7][ch] + kSH2[4] * 2.f * x * sh[8][ch];
+                            dRGBdy[ch] += kSH2[0] * x * sh[4][ch] + kSH2[1] * z * sh[5][ch] + kSH2[2] * 2.f * -y * sh[6][ch] + kSH2[4] * 2.f * -y * sh[8][ch];
+                            dRGBdz[ch] += kSH2[1] * y * sh[5][ch] + kSH2[2] * 2.f * 2.f * z * sh[6][ch] + kSH2[3] * x * sh[7][ch];
+                        }
+                        if (DEG > 2) {
+                            const float b9 = kSH3[0] * y * (3.f * xx - yy), b10 = kSH3[1] * xy * z;
+                            const float b11 = kSH3[2] * y * (4.f * zz - xx - yy);
+                            const float b12 = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                            const float b13 = kSH3[4] * x * (4.f * zz - xx - yy), b14 = kSH3[5] * z * (xx - yy);
+                            const float b15 = kSH3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+                            for (int ch = 0; ch < 3; ch++) {
+                                dsh[9][ch] += b9 * dRGB[ch]; dsh[10][ch] += b10 * dRGB[ch]; dsh[11][ch] += b11 * dRGB[ch];
+                                dsh[12][ch] += b12 * dRGB[ch]; dsh[13][ch] += b13 * dRGB[ch]; dsh[14][ch] += b14 * dRGB[ch];
+                                dsh[15][ch] += b15 * dRGB[ch];
+                                dRGBdx[ch] += (kSH3[0] * sh[9][ch] * 3.f * 2.f * xy + kSH3[1] * sh[10][ch] * yz +
+                                               kSH3[2] * sh[11][ch] * -2.f * xy + kSH3[3] * sh[12][ch] * -3.f * 2.f * xz +
+                                               kSH3[4] * sh[13][ch] * (-3.f * xx + 4.f * zz - yy) +
+                                               kSH3[5] * sh[14][ch] * 2.f * xz + kSH3[6] * sh[15][ch] * 3.f * (xx - yy));
+                                dRGBdy[ch] += (kSH3[0] * sh[9][ch] * 3.f * (xx - yy) + kSH3[1] * sh[10][ch] * xz +
+                                               kSH3[2] * sh[11][ch] * (-3.f * yy + 4.f * zz - xx) +
+                                               kSH3[3] * sh[12][ch] * -3.f * 2.f * yz + kSH3[4] * sh[13][ch] * -2.f * xy +
+                                               kSH3[5] * sh[14][ch] * -2.f * yz + kSH3[6] * sh[15][ch] * -3.f * 2.f * xy);
+                                dRGBdz[ch] += (kSH3[1] * sh[10][ch] * xy + kSH3[2] * sh[11][ch] * 4.f * 2.f * yz +
+                                               kSH3[3] * sh[12][ch] * 3.f * (2.f * zz - xx - yy) +
+                                               kSH3[4] * sh[13][ch] * 4.f * 2.f * xz + kSH3[5] * sh[14][ch] * (xx - yy));
+                            }
+                        }
+                    }
+                }
+                const float3 dL_ddir = {dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
+                                        dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
+                                        dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]};
+                // gradient through the normalisation of the view direction
+                const float3 vv = dir_orig;
+                const float sum2 = vv.x * vv.x + vv.y * vv.y + vv.z * vv.z;
+                const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+                dm.x += ((+sum2 - vv.x * vv.x) * dL_ddir.x - vv.y * vv.x * dL_ddir.y - vv.z * vv.x * dL_ddir.z) * invsum32;
+                dm.y += (-vv.x * vv.y * dL_ddir.x + (sum2 - vv.y * vv.y) * dL_ddir.y - vv.z * vv.y * dL_ddir.z) * invsum32;
+                dm.z += (-vv.x * vv.z * dL_ddir.x - vv.y * vv.z * dL_ddir.y + (sum2 - vv.z * vv.z) * dL_ddir.z) * invsum32;
+            } else {
+                dcolor_acc.x += dcol.x; dcolor_acc.y += dcol.y; dcolor_acc.z += dcol.z;
+            }
+            dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
+        }
+        // pose gradients of this sub-frame: warp reduce, then fp64 atomics
+        const float total = HalvingReduce<NPOSE>::run(pv, lane);
+        if (my_slot >= 0) atomicAdd(p.pose_acc + (size_t)s * 32 + my_slot, (double)total);
+    }
+    if (!live) return;
+
+    p.dL_dmeans3D[3 * g] = dmean.x; p.dL_dmeans3D[3 * g + 1] = dmean.y; p.dL_dmeans3D[3 * g + 2] = dmean.z;
+    p.dL_dopacity[g] = dopac;
+    if (DEG >= 0) {
+        float* dst = p.dL_dsh + (size_t)g * f.M * 3;
+#pragma unroll
+        for (int k = 0; k < NC; k++) { dst[3 * k] = dsh[k][0]; dst[3 * k + 1] = dsh[k][1]; dst[3 * k + 2] = dsh[k][2]; }
+        for (int k = NC; k < f.M; k++) { dst[3 * k] = 0.f; dst[3 * k + 1] = 0.f; dst[3 * k + 2] = 0.f; }
+    } else if (p.dL_dcolors_precomp) {
+        p.dL_dcolors_precomp[3 * g] = dcolor_acc.x; p.dL_dcolors_precomp[3 * g + 1] = dcolor_acc.y;
+        p.dL_dcolors_precomp[3 * g + 2] = dcolor_acc.z;
+    }
+    if (f.cov3D_precomp != nullptr) {
+        if (p.dL_dcov3D_precomp) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) p.dL_dcov3D_precomp[6 * (size_t)g + i] = dcov[i];
+        }
+    } else {
+        // cov3D -> scale / rotation (reference backward.cu:299-362); linear in dL/dcov3D, so
+        // it is applied once to the sum over sub-frames.
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        Mat3 R;
+        R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+        R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+        R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+        const float3 sv = {f.scale_modifier * scale.x, f.scale_modifier * scale.y, f.scale_modifier * scale.z};
+        Mat3 S;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) S.m[c][rr] = 0.f;
+        S.m[0][0] = sv.x; S.m[1][1] = sv.y; S.m[2][2] = sv.z;
+        const Mat3 Mm = mat3_mul(S, R);
+        Mat3 dSigma;
+        dSigma.m[0][0] = dcov[0];        dSigma.m[0][1] = 0.5f * dcov[1]; dSigma.m[0][2] = 0.5f * dcov[2];
+        dSigma.m[1][0] = 0.5f * dcov[1]; dSigma.m[1][1] = dcov[3];        dSigma.m[1][2] = 0.5f * dcov[4];
+        dSigma.m[2][0] = 0.5f * dcov[2]; dSigma.m[2][1] = 0.5f * dcov[4]; dSigma.m[2][2] = dcov[5];
+        Mat3 M2;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) M2.m[c][rr] = 2.0f * Mm.m[c][rr];
+        const Mat3 dL_dM = mat3_mul(M2, dSigma);
+        const Mat3 Rt = mat3_transpose(R);
+        Mat3 dMt = mat3_transpose(dL_dM);
+        p.dL_dscales[3 * g]     = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+        p.dL_dscales[3 * g + 1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+        p.dL_dscales[3 * g + 2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) { dMt.m[0][rr] *= sv.x; dMt.m[1][rr] *= sv.y; dMt.m[2][rr] *= sv.z; }
+        float4 dq;
+        dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+        dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+        dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+        dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        reinterpret_cast<float4*>(p.dL_drotations)[g] = dq;
+    }
+}
+
+// pose_acc [F,32] fp64 -> dL_dview [F,16], dL_dproj [F,16] fp32
+__global__ void k_pose_finalize(const double* __restrict__ acc, int F, float* __restrict__ dview,
+                                float* __restrict__ dproj)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * 32) return;
+    const int s = i / 32, e = i % 32;
+    if (e < 16) {
+        dview[s * 16 + e] = (float)acc[s * 32 + e];
+    } else {
+        const int k = e - 16;
+        // entries 3,7,11,15 of the projection gradient all carry the shared last-row term
+        const double v = ((k & 3) == 3) ? acc[s * 32 + 19] : acc[s * 32 + e];
+        dproj[s * 16 + k] = (float)v;
+    }
+}
+
+void launch_preprocess_bwd(const BwdParams& p, int sh_degree, cudaStream_t st)
+{
+    const FwdParams& f = p.f;
+    if (f.P > 0 && f.F > 0) {
+        dim3 grid((f.P + 255) / 256), block(256);
+        const float* grad = reinterpret_cast<const float*>(p.g0);
+        if (f.colors_precomp != nullptr) {
+            k_preprocess_bwd<-1><<<grid, block, 0, st>>>(p, grad);
+        } else {
+            switch (sh_degree) {
+                case 0: k_preprocess_bwd<0><<<grid, block, 0, st>>>(p, grad); break;
+                case 1: k_preprocess_bwd<1><<<grid, block, 0, st>>>(p, grad); break;
+                case 2: k_preprocess_bwd<2><<<grid, block, 0, st>>>(p, grad); break;
+                default: k_preprocess_bwd<3><<<grid, block, 0, st>>>(p, grad); break;
+            }
+        }
+    }
+    if (f.F > 0) k_pose_finalize<<<(f.F * 32 + 255) / 256, 256, 0, st>>>(p.pose_acc, f.F, p.dL_dview, p.dL_dproj);
+}
+
+}  // namespace dgs

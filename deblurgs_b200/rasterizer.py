@@ -1,0 +1,316 @@
+"""Drop-in for the reference's `diff_gaussian_rasterization` Python package, backed by
+libdgs_b200.so through its C-ABI.
+
+Mirrors submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py of
+taekkii/deblurgs: `GaussianRasterizationSettings` (same 13 fields, same order, :172-187),
+`GaussianRasterizer` (same forward kwargs / 3-tuple return / error messages, :189-241),
+`_RasterizeGaussians` (same saved state and gradient tuple order, :48-170) -- plus the batched
+`rasterize_blurry` that renders all F sub-frames of a blurry view in one call.
+"""
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    z_near: float
+    z_far: float
+    use_sigmoid: bool
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class _Buffer:
+    """Growable device byte buffer handed to the library's resize callback (the reference's
+    `resizeFunctional`, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, nbytes):
+        try:
+            self.t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.t.data_ptr()
+        except Exception:  # never let an exception cross the C boundary
+            return 0
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.DgsError("%s must be a CUDA tensor: libdgs_b200 has no CPU path" % name)
+
+
+def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                     viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy, scale_modifier,
+                     z_near, z_far, sh_degree, prefiltered, use_sigmoid, want_blur, blur_denominator):
+    """Runs dgs_blur_forward. viewmatrix/projmatrix [F,4,4], campos [F,3]."""
+    lib = _lib.load()
+    _require_cuda(means3D, "means3D")
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise _lib.DgsError("means3D must have dimensions (num_points, 3)")
+    dev = means3D.device
+    P = means3D.shape[0]
+    F = viewmatrix.shape[0]
+    M = sh.shape[1] if (sh is not None and sh.numel() != 0) else 0
+    color = torch.empty((F, 3, H, W), dtype=torch.float32, device=dev)
+    depth = torch.empty((F, 1, H, W), dtype=torch.float32, device=dev)
+    radii = torch.empty((F, P), dtype=torch.int32, device=dev)
+    blur = torch.empty((3, H, W), dtype=torch.float32, device=dev) if want_blur else None
+    geom, binning, img = _Buffer(dev), _Buffer(dev), _Buffer(dev)
+    num_rendered = C.c_int64(0)
+    if P == 0:
+        # reference: kernels skipped, zero images returned (rasterize_points.cu:85)
+        color.zero_()
+        depth.zero_()
+        if blur is not None:
+            blur.zero_()
+        return color, depth, radii, blur, 0, geom.t, binning.t, img.t
+    with torch.cuda.device(dev):
+        rc = lib.dgs_blur_forward(
+            geom.cb, None, binning.cb, None, img.cb, None,
+            P, F, int(sh_degree), int(M),
+            _lib.ptr(bg), int(W), int(H),
+            _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors_precomp),
+            _lib.ptr(opacities), _lib.ptr(scales), float(scale_modifier),
+            _lib.ptr(rotations), _lib.ptr(cov3Ds_precomp),
+            _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos),
+            float(tanfovx), float(tanfovy), float(z_near), float(z_far),
+            int(bool(prefiltered)), int(bool(use_sigmoid)),
+            _lib.ptr(color), _lib.ptr(depth), _lib.ptr(radii),
+            _lib.ptr(blur), float(blur_denominator),
+            C.byref(num_rendered), _stream_ptr(dev))
+    _lib.check(rc, "dgs_blur_forward")
+    return color, depth, radii, blur, int(num_rendered.value), geom.t, binning.t, img.t
+
+
+def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacities, scales, rotations,
+                      cov3Ds_precomp, viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy,
+                      scale_modifier, z_near, z_far, sh_degree, use_sigmoid, radii, geom, binning, img,
+                      grad_color, grad_depth, want_means2D):
+    lib = _lib.load()
+    dev = means3D.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    has_sh = sh is not None and sh.numel() != 0
+    has_colors = colors_precomp is not None and colors_precomp.numel() != 0
+    has_scales = scales is not None and scales.numel() != 0
+    has_cov = cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0
+    dmeans2D = torch.empty((F, P, 3), **f32) if want_means2D else None
+    dmeans3D = torch.zeros((P, 3), **f32)
+    dsh = torch.zeros((P, M, 3), **f32) if has_sh else torch.zeros((P, 0, 3), **f32)
+    dopacity = torch.zeros((P, 1), **f32)
+    dscales = torch.zeros((P, 3), **f32) if has_scales else None
+    drot = torch.zeros((P, 4), **f32) if has_scales else None
+    dcolors = torch.zeros((P, 3), **f32) if has_colors else None
+    dcov = torch.zeros((P, 6), **f32) if has_cov else None
+    dview = torch.zeros((F, 4, 4), **f32)
+    dproj = torch.zeros((F, 4, 4), **f32)
+    if P == 0 or F == 0:
+        return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj
+    scratch = torch.empty(int(lib.dgs_blur_backward_scratch_bytes(P, F)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.dgs_blur_backward(
+            P, F, int(sh_degree), int(M), int(num_rendered),
+            _lib.ptr(bg), int(W), int(H),
+            _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors_precomp),
+            _lib.ptr(opacities), _lib.ptr(scales), float(scale_modifier),
+            _lib.ptr(rotations), _lib.ptr(cov3Ds_precomp),
+            _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos),
+            float(tanfovx), float(tanfovy), float(z_near), float(z_far), int(bool(use_sigmoid)),
+            _lib.ptr(radii), _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img),
+            _lib.ptr(grad_color), _lib.ptr(grad_depth), _lib.ptr(scratch),
+            _lib.ptr(dmeans2D), _lib.ptr(dmeans3D), _lib.ptr(dsh), _lib.ptr(dopacity),
+            _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
+            _lib.ptr(dview), _lib.ptr(dproj), _stream_ptr(dev))
+    _lib.check(rc, "dgs_blur_backward")
+    return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj
+
+
+def _empty_like_input(t):
+    return torch.zeros_like(t) if (t is not None and t.numel() != 0) else None
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """Single view. Same argument order, saved state and gradient tuple as the reference's
+    `_RasterizeGaussians` (diff_gaussian_rasterization/__init__.py:48-170)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, viewmatrix, projmatrix, raster_settings):
+        rs = raster_settings
+        means3D_c, sh_c, colors_c = _f32c(means3D), _f32c(sh), _f32c(colors_precomp)
+        opac_c, scales_c, rot_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
+        view_c = _f32c(viewmatrix).reshape(1, 4, 4)
+        proj_c = _f32c(projmatrix).reshape(1, 4, 4)
+        campos_c = _f32c(rs.campos).reshape(1, 3)
+        bg_c = _f32c(rs.bg)
+        color, depth, radii, _, num_rendered, geom, binning, img = _forward_batched(
+            means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, view_c, proj_c, campos_c, bg_c,
+            rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near,
+            rs.z_far, rs.sh_degree, rs.prefiltered, rs.use_sigmoid, False, 1.0)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, opac_c, geom, binning,
+                              img, view_c, proj_c, campos_c, bg_c)
+        ctx.mark_non_differentiable(radii)
+        return color[0], depth[0], radii[0]
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth, _):
+        rs = ctx.raster_settings
+        (colors_c, means3D, scales, rot, cov, radii, sh, opac, geom, binning, img, view, proj, campos,
+         bg) = ctx.saved_tensors
+        P = means3D.shape[0]
+        M = sh.shape[1] if sh.numel() != 0 else 0
+        gc = _f32c(grad_out_color) if grad_out_color is not None else None
+        gd = _f32c(grad_out_depth) if grad_out_depth is not None else None
+        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj) = _backward_batched(
+            P, 1, M, ctx.num_rendered, means3D, sh, colors_c, opac, scales, rot, cov, view, proj, campos, bg,
+            rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
+            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, True)
+        # reference order: means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+        # cov3Ds_precomp, viewmatrix, projmatrix, raster_settings
+        return (dmeans3D, dmeans2D[0], dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
+                dview[0], dproj[0], None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        viewmatrix, projmatrix, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, viewmatrix, projmatrix, raster_settings)
+
+
+class _RasterizeBlurry(torch.autograd.Function):
+    """All F sub-frames of one blurry view. Inputs as `_RasterizeGaussians` except that
+    viewmatrix/projmatrix are [F,4,4], campos [F,3] is explicit (no gradient, as in the
+    reference where it rides in the settings tuple) and means2D is an [F,P,3] gradient sink.
+    Returns (color [F,3,H,W], depth [F,1,H,W], radii [F,P], blurred [3,H,W])."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                viewmatrix, projmatrix, campos, raster_settings, blur_denominator):
+        rs = raster_settings
+        means3D_c, sh_c, colors_c = _f32c(means3D), _f32c(sh), _f32c(colors_precomp)
+        opac_c, scales_c, rot_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
+        view_c, proj_c, campos_c, bg_c = _f32c(viewmatrix), _f32c(projmatrix), _f32c(campos), _f32c(rs.bg)
+        F = view_c.shape[0]
+        denom = float(blur_denominator) if blur_denominator else float(F)
+        color, depth, radii, blur, num_rendered, geom, binning, img = _forward_batched(
+            means3D_c, sh_c, colors_c, opac_c, scales_c, rot_c, cov_c, view_c, proj_c, campos_c, bg_c,
+            rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near,
+            rs.z_far, rs.sh_degree, rs.prefiltered, rs.use_sigmoid, True, denom)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.denom = denom
+        ctx.want_means2D = means2D is not None and means2D.requires_grad
+        ctx.save_for_backward(colors_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, opac_c, geom, binning,
+                              img, view_c, proj_c, campos_c, bg_c)
+        ctx.mark_non_differentiable(radii)
+        return color, depth, radii, blur
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_depth, _radii, grad_blur):
+        rs = ctx.raster_settings
+        (colors_c, means3D, scales, rot, cov, radii, sh, opac, geom, binning, img, view, proj, campos,
+         bg) = ctx.saved_tensors
+        P = means3D.shape[0]
+        F = view.shape[0]
+        M = sh.shape[1] if sh.numel() != 0 else 0
+        gc = _f32c(grad_color) if grad_color is not None else None
+        if grad_blur is not None:
+            # blurred = sum_s color_s / denom  =>  dL/dcolor_s += dL/dblurred / denom
+            gb = (_f32c(grad_blur) / ctx.denom).unsqueeze(0)
+            gc = gb.expand(F, -1, -1, -1).contiguous() if gc is None else gc + gb
+        gd = _f32c(grad_depth) if grad_depth is not None else None
+        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj) = _backward_batched(
+            P, F, M, ctx.num_rendered, means3D, sh, colors_c, opac, scales, rot, cov, view, proj, campos, bg,
+            rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
+            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D)
+        return (dmeans3D, dmeans2D, dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
+                dview, dproj, None, None, None)
+
+
+def rasterize_blurry(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                     viewmatrix, projmatrix, campos, raster_settings, blur_denominator=None):
+    empty = torch.Tensor([])
+    return _RasterizeBlurry.apply(
+        means3D, means2D, sh if sh is not None else empty,
+        colors_precomp if colors_precomp is not None else empty, opacities,
+        scales if scales is not None else empty, rotations if rotations is not None else empty,
+        cov3Ds_precomp if cov3Ds_precomp is not None else empty,
+        viewmatrix, projmatrix, campos, raster_settings, blur_denominator)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions, viewmatrix=None, projmatrix=None):
+        """Frustum test. The reference reads `raster_settings.viewmatrix`, a field that no longer
+        exists (dead code); here the matrices are explicit arguments."""
+        lib = _lib.load()
+        with torch.no_grad():
+            positions = _f32c(positions)
+            _require_cuda(positions, "positions")
+            if viewmatrix is None:
+                viewmatrix = getattr(self.raster_settings, "viewmatrix")  # AttributeError like the reference
+                projmatrix = getattr(self.raster_settings, "projmatrix")
+            P = positions.shape[0]
+            present = torch.zeros(P, dtype=torch.uint8, device=positions.device)
+            with torch.cuda.device(positions.device):
+                rc = lib.dgs_mark_visible(P, _lib.ptr(positions), _lib.ptr(_f32c(viewmatrix)),
+                                          _lib.ptr(_f32c(projmatrix)) if projmatrix is not None else None,
+                                          _lib.ptr(present), _stream_ptr(positions.device))
+            _lib.check(rc, "dgs_mark_visible")
+        return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, viewmatrix=None, projmatrix=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, viewmatrix, projmatrix, raster_settings)

@@ -1,0 +1,202 @@
+/*
+ * dgs_b200.h -- C-ABI of libdgs_b200.so, the B200-native (sm_100a) blurry-view
+ * Gaussian-splatting rasterizer.  Every entry point is `extern "C"`, takes plain
+ * device pointers + sizes + a cudaStream_t (passed as void*), returns 0 on success
+ * or a negative dgs_status whose text is available from dgs_last_error().
+ *
+ * What each entry point replaces in the reference (taekkii/deblurgs):
+ *   dgs_forward / dgs_backward
+ *       pybind `rasterize_gaussians` / `rasterize_gaussians_backward`
+ *       (submodules/diff-gaussian-rasterization/ext.cpp:15-19, rasterize_points.cu:35-218)
+ *       = CudaRasterizer::Rasterizer::forward / backward
+ *       (cuda_rasterizer/rasterizer.h:31-95, rasterizer_impl.cu:198-463)
+ *   dgs_blur_forward / dgs_blur_backward
+ *       the Python loop `for cam in subframe_cams: render(cam, gaussians, bg)` + stack + mean
+ *       of CameraMotionModule.query (scene/motion.py:138-150) and the F autograd backward
+ *       calls it induces (diff_gaussian_rasterization/__init__.py:111-170)
+ *   dgs_pose_forward / dgs_pose_backward
+ *       BezierModel.forward (scene/bezier.py:54-83), se3_exp_map
+ *       (utils/pytorch3d_functions.py:373-457), _c2w_to_minicam (scene/motion.py:258-294),
+ *       MiniCam.__init__ (scene/cameras.py:63-74) and their autograd
+ *   dgs_mark_visible        pybind `mark_visible` (ext.cpp:18, rasterizer_impl.cu:54-66,141-153)
+ *   dgs_knn_mean_dist2      `distCUDA2` (submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221)
+ *
+ * Memory ownership follows the reference (rasterize_points.cu:27-33,80-82): the caller
+ * owns every buffer; the library asks for its three opaque state buffers through resize
+ * callbacks and hands them back for the backward pass.
+ *
+ * Matrix convention = the reference's: `viewmatrix`/`projmatrix` are the row-major torch
+ * tensors world_view_transform / full_proj_transform, i.e. element [4*col + row] of the
+ * mathematical matrix (cuda_rasterizer/auxiliary.h:58-77).
+ */
+#ifndef DGS_B200_H_INCLUDED
+#define DGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dgs_status {
+    DGS_OK = 0,
+    DGS_ERR_INVALID_ARGUMENT = -1,
+    DGS_ERR_CUDA = -2,
+    DGS_ERR_ALLOC = -3,
+    DGS_ERR_UNSUPPORTED = -4
+} dgs_status;
+
+/* Resize callback: must return a device pointer to at least `bytes` bytes, 128-B aligned,
+ * that stays valid until the matching backward has run.  (Reference: the three
+ * std::function<char*(size_t)> of Rasterizer::forward, rasterizer.h:32-34.) */
+typedef char* (*dgs_alloc_fn)(void* ctx, size_t bytes);
+
+/* Library / build introspection. */
+const char* dgs_last_error(void);
+int dgs_version(void);            /* 100 * major + minor */
+int dgs_compiled_arch(void);      /* 1000 for sm_100a */
+
+/*
+ * Batched forward: F sub-frames of one blurry view over the same P Gaussians.
+ *   view/proj   [F,16]   campos [F,3]   (device, fp32)
+ *   out_color   [F,3,H,W]   out_depth [F,1,H,W]   radii [F,P] int32
+ *   out_blur    [3,H,W] or NULL: (1/F_total) * sum_s out_color[s]   (F_total = blur_denominator,
+ *               so a rank that renders a shard of the sub-frames produces its partial mean)
+ * Optional inputs follow the reference: exactly one of shs / colors_precomp and exactly one
+ * of (scales, rotations) / cov3D_precomp is non-NULL.  sh_degree = active degree D (0..3),
+ * sh_coeffs = M (allocated coefficients per Gaussian, >= (D+1)^2).
+ * Returns the total number of (Gaussian, tile) duplicates over all F sub-frames in
+ * *num_rendered (the reference's per-sub-frame `num_rendered`, summed).
+ */
+int dgs_blur_forward(
+    dgs_alloc_fn geom_alloc, void* geom_ctx,
+    dgs_alloc_fn binning_alloc, void* binning_ctx,
+    dgs_alloc_fn image_alloc, void* image_ctx,
+    int P, int F, int sh_degree, int sh_coeffs,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far,
+    int prefiltered, int use_sigmoid,
+    float* out_color, float* out_depth, int* radii,
+    float* out_blur, float blur_denominator,
+    int64_t* num_rendered, void* stream);
+
+/*
+ * Batched backward.  dL_dpix [F,3,H,W], dL_dpixdepth [F,1,H,W] (either may be NULL = zeros).
+ * Gaussian gradients are SUMMED over the F sub-frames and written (not accumulated):
+ *   dL_dmeans3D [P,3] dL_dsh [P,M,3] dL_dopacity [P,1] dL_dscales [P,3] dL_drotations [P,4]
+ *   dL_dcolors_precomp [P,3] dL_dcov3D_precomp [P,6]   (only with the matching precomp input)
+ * Per-sub-frame outputs:
+ *   dL_dmeans2D [F,P,3] (x,y = gradient w.r.t. NDC, z = 0; reference backward.cu:628-629) or NULL
+ *   dL_dviewmatrix [F,16], dL_dprojmatrix [F,16]  (reference quirks reproduced)
+ * `scratch` must hold dgs_blur_backward_scratch_bytes(P,F) bytes; contents undefined on return.
+ */
+size_t dgs_blur_backward_scratch_bytes(int P, int F);
+
+int dgs_blur_backward(
+    int P, int F, int sh_degree, int sh_coeffs, int64_t num_rendered,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
+    const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpixdepth,
+    char* scratch,
+    float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
+    float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
+    float* dL_dviewmatrix, float* dL_dprojmatrix, void* stream);
+
+/* Single-view pair: the reference's rasterize_gaussians / rasterize_gaussians_backward
+ * (same argument meaning; F = 1 instance of the batched pair). */
+int dgs_forward(
+    dgs_alloc_fn geom_alloc, void* geom_ctx,
+    dgs_alloc_fn binning_alloc, void* binning_ctx,
+    dgs_alloc_fn image_alloc, void* image_ctx,
+    int P, int sh_degree, int sh_coeffs,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far,
+    int prefiltered, int use_sigmoid,
+    float* out_color, float* out_depth, int* radii,
+    int64_t* num_rendered, void* stream);
+
+int dgs_backward(
+    int P, int sh_degree, int sh_coeffs, int64_t num_rendered,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
+    const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpixdepth,
+    char* scratch,
+    float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
+    float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
+    float* dL_dviewmatrix, float* dL_dprojmatrix, void* stream);
+
+/*
+ * Debug/parity accessors: decode the opaque state buffers of a forward call into the
+ * reference's per-sub-frame quantities (GeometryState / BinningState / ImageState,
+ * rasterizer_impl.h:31-63).  All outputs optional (NULL = skip).
+ *   depths [F,P] means2D [F,P,2] conic_opacity [F,P,4] rgb [F,P,3] clamped [F,P,3]
+ *   tiles_touched [F,P] u32   point_offsets [F,P] u32 (inclusive scan over the whole batch)
+ */
+int dgs_debug_geometry(const char* geom_buffer, int P, int F,
+                       float* depths, float* means2D, float* conic_opacity, float* rgb,
+                       float* clamped, uint32_t* tiles_touched, uint32_t* point_offsets,
+                       void* stream);
+/*   keys [D] u64 (batched key: sub-frame | tile | depth bits), point_list [D] u32 */
+int dgs_debug_binning(const char* binning_buffer, int64_t num_rendered,
+                      uint64_t* keys, uint32_t* point_list, void* stream);
+/*   ranges [F,tiles,2] u32 (absolute positions in the batched list), final_T [F,H,W],
+ *   n_contrib [F,H,W] u32 */
+int dgs_debug_image(const char* image_buffer, int F, int width, int height,
+                    uint32_t* ranges, float* final_T, uint32_t* n_contrib, void* stream);
+/* Number of key bits used for the tile id and the sub-frame id of the batched sort key. */
+int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bits);
+
+/*
+ * Sub-frame poses from Bezier control points in se(3) (curve_type == "se3").
+ *   ctrl_trans, ctrl_rot [C+1,3] fp32 (control point k weighted by binom(C,k) t^(C-k) (1-t)^k)
+ *   nu [F] fp32 in [0,1];  proj_t [16] = the reference camera's `projection_matrix`
+ *   (getProjectionMatrix(...).T, row-major)
+ * Outputs: viewmatrix [F,16], projmatrix [F,16], campos [F,3] (fp32), and `jacobian`
+ * [F, 35, 7] fp64: d(view 16 | proj 16 | campos 3)/d(se3 6-vector u|omega, nu) in the
+ * reference's autograd semantics (campos rows are zero: the reference gives no gradient).
+ */
+int dgs_pose_forward(int F, int curve_order,
+                     const float* ctrl_trans, const float* ctrl_rot, const float* nu,
+                     const float* proj_t,
+                     float* viewmatrix, float* projmatrix, float* campos,
+                     double* jacobian, void* stream);
+/*   dL_dctrl_trans, dL_dctrl_rot [C+1,3] fp32, dL_dnu [F] fp32 (written, not accumulated) */
+int dgs_pose_backward(int F, int curve_order,
+                      const float* ctrl_trans, const float* ctrl_rot, const float* nu,
+                      const double* jacobian,
+                      const float* dL_dviewmatrix, const float* dL_dprojmatrix,
+                      float* dL_dctrl_trans, float* dL_dctrl_rot, float* dL_dnu, void* stream);
+
+/* present [P] uint8: 1 iff view-space z > 0.2 (reference in_frustum, auxiliary.h:144-169). */
+int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Mean squared distance to the 3 nearest neighbours (exact). scratch: dgs_knn_scratch_bytes(P). */
+size_t dgs_knn_scratch_bytes(int P);
+int dgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGS_B200_H_INCLUDED */
