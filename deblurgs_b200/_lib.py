@@ -40,6 +40,12 @@ SIGNATURES = {
     "dgs_debug_geometry": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_debug_binning": (_i, [_p, _i64, _p, _p, _p]),
     "dgs_debug_image": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "dgs_profile_enable": (_i, [_i]),
+    "dgs_profile_num_stages": (_i, []),
+    "dgs_profile_stage_name": (C.c_char_p, [_i]),
+    "dgs_profile_read": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), _i, _i]),
+    "dgs_launch_count": (_i64, [_i]),
+    "dgs_debug_workload": (_i, [_p, _p, _p, _i, _i, _i, _i, _i64, _p, _p]),
     "dgs_pose_forward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_pose_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace dgs {
 
@@ -29,6 +30,39 @@ static int fail_cuda(cudaError_t e, const char* where)
         cudaError_t e__ = (call);                               \
         if (e__ != cudaSuccess) return fail_cuda(e__, where);   \
     } while (0)
+
+// ---- stage profiling ---------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int stage; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static double g_stage_ms[ST_COUNT];
+static long long g_stage_calls[ST_COUNT];
+static long long g_own_launches = 0;
+static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges",
+                                            "render_fwd", "blur_mean", "bwd_memset", "render_bwd",
+                                            "preprocess_bwd", "pose_fwd", "pose_bwd"};
+static cudaEvent_t get_event()
+{
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+StageTimer::StageTimer(int stage, cudaStream_t st_, int own_kernels) : idx(-1), st(st_)
+{
+    g_own_launches += own_kernels;
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.a = get_event(); r.b = get_event(); r.stage = stage;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    idx = (int)g_prof.size() - 1;
+}
+StageTimer::~StageTimer()
+{
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+}
 
 static int bits_for(uint32_t n)  // number of bits needed to hold values 0..n-1 (>= 1)
 {
@@ -202,9 +236,12 @@ int dgs_blur_forward(
 
     int64_t D = 0;
     if (N > 0) {
-        launch_preprocess_fwd(p, sh_degree, st);
+        { StageTimer t(ST_PREPROCESS_FWD, st, 1); launch_preprocess_fwd(p, sh_degree, st); }
         size_t tmp = G.scan_temp_bytes;
-        DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, p.tiles, p.offsets, (int64_t)N, st), "scan");
+        {
+            StageTimer t(ST_SCAN, st, 0);
+            DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, p.tiles, p.offsets, (int64_t)N, st), "scan");
+        }
         uint32_t total = 0;
         // The one host synchronisation of the batched forward (the reference does one per
         // sub-frame, rasterizer_impl.cu:287): the binning buffer is sized from it.
@@ -226,16 +263,19 @@ int dgs_blur_forward(
     if (F > 0 && tiles > 0)
         DGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)F * tiles * sizeof(uint2), st), "ranges memset");
     if (D > 0) {
-        launch_duplicate(p, keys_unsorted, vals_unsorted, st);
+        { StageTimer t(ST_DUPLICATE, st, 1); launch_duplicate(p, keys_unsorted, vals_unsorted, st); }
         size_t tmp = B.sort_temp_bytes;
-        DGS_CUDA(cub::DeviceRadixSort::SortPairs(bin + B.sort_temp, tmp, keys_unsorted, keys, vals_unsorted,
-                                                 point_list, (int64_t)D, 0, 32 + p.tile_bits + sf_bits, st),
-                 "radix sort");
-        launch_tile_ranges(D, keys, p.tile_bits, (int)tiles, ranges, st);
+        {
+            StageTimer t(ST_SORT, st, 0);
+            DGS_CUDA(cub::DeviceRadixSort::SortPairs(bin + B.sort_temp, tmp, keys_unsorted, keys, vals_unsorted,
+                                                     point_list, (int64_t)D, 0, 32 + p.tile_bits + sf_bits, st),
+                     "radix sort");
+        }
+        { StageTimer t(ST_TILE_RANGES, st, 1); launch_tile_ranges(D, keys, p.tile_bits, (int)tiles, ranges, st); }
     }
     if (F > 0 && pixels > 0) {
-        launch_render_fwd(p, ranges, point_list, final_T, n_contrib, out_color, out_depth, st);
-        if (out_blur) launch_blur_mean(out_color, F, 3 * pixels, blur_denominator, out_blur, st);
+        { StageTimer t(ST_RENDER_FWD, st, 1); launch_render_fwd(p, ranges, point_list, final_T, n_contrib, out_color, out_depth, st); }
+        if (out_blur) { StageTimer t(ST_BLUR_MEAN, st, 1); launch_blur_mean(out_color, F, 3 * pixels, blur_denominator, out_blur, st); }
     }
     DGS_CUDA(cudaGetLastError(), "forward launch");
     return DGS_OK;
@@ -308,9 +348,12 @@ int dgs_blur_backward(
     b.dL_dcolors_precomp = dL_dcolors_precomp; b.dL_dcov3D_precomp = dL_dcov3D_precomp;
     b.dL_dview = dL_dviewmatrix; b.dL_dproj = dL_dprojmatrix;
 
-    DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
-    if (num_rendered > 0 && pixels > 0) launch_render_bwd(b, st);
-    launch_preprocess_bwd(b, sh_degree, st);
+    {
+        StageTimer t(ST_BWD_MEMSET, st, 0);
+        DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
+    }
+    if (num_rendered > 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
+    { StageTimer t(ST_PREPROCESS_BWD, st, 2); launch_preprocess_bwd(b, sh_degree, st); }
     DGS_CUDA(cudaGetLastError(), "backward launch");
     return DGS_OK;
 }
@@ -358,6 +401,82 @@ int dgs_backward(
                              radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpixdepth, scratch,
                              dL_dmeans2D, dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations,
                              dL_dcolors_precomp, dL_dcov3D_precomp, dL_dviewmatrix, dL_dprojmatrix, stream);
+}
+
+// ---- profiling / measurement ------------------------------------------------------------
+int dgs_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    return DGS_OK;
+}
+int dgs_profile_num_stages(void) { return ST_COUNT; }
+const char* dgs_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+int dgs_profile_read(double* ms, int64_t* calls, int n, int reset)
+{
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess) return fail_cuda(e, "profile read");
+        g_stage_ms[r.stage] += t;
+        g_stage_calls[r.stage] += 1;
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    for (int i = 0; i < n && i < ST_COUNT; i++) {
+        if (ms) ms[i] = g_stage_ms[i];
+        if (calls) calls[i] = g_stage_calls[i];
+    }
+    if (reset) {
+        for (int i = 0; i < ST_COUNT; i++) { g_stage_ms[i] = 0.0; g_stage_calls[i] = 0; }
+    }
+    return DGS_OK;
+}
+int64_t dgs_launch_count(int reset)
+{
+    const int64_t v = g_own_launches;
+    if (reset) g_own_launches = 0;
+    return v;
+}
+void dgs_profile_note(int stage, void* stream, int own_kernels, int begin, int* token)
+{
+    // used by translation units that cannot see StageTimer's storage (pose kernels)
+    if (begin) {
+        StageTimer* t = new StageTimer(stage, (cudaStream_t)stream, own_kernels);
+        *token = t->idx;
+        t->idx = -1;   // do not record the end event on destruction
+        delete t;
+    } else if (*token >= 0 && *token < (int)g_prof.size()) {
+        cudaEventRecord(g_prof[*token].b, (cudaStream_t)stream);
+    }
+}
+
+int dgs_debug_workload(const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                       int P, int F, int width, int height, int64_t num_rendered, uint64_t* out_dev,
+                       void* stream)
+{
+    if (F == 0 || P == 0) return DGS_OK;
+    if (!geom_buffer || !binning_buffer || !image_buffer || !out_dev) return fail(DGS_ERR_INVALID_ARGUMENT, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = P; p.F = F; p.W = width; p.H = height;
+    p.tiles_x = (width + DGS_TILE_X - 1) / DGS_TILE_X;
+    p.tiles_y = (height + DGS_TILE_Y - 1) / DGS_TILE_Y;
+    const size_t N = (size_t)P * F, tiles = (size_t)p.tiles_x * p.tiles_y, pixels = (size_t)width * height;
+    const GeomLayout G = geom_layout(N);
+    const ImgLayout I = img_layout(F, tiles, pixels);
+    const BinLayout B = bin_layout((size_t)num_rendered);
+    char* geom = aligned128((char*)geom_buffer);
+    char* img = aligned128((char*)image_buffer);
+    char* bin = aligned128((char*)binning_buffer);
+    bind_geom(p, geom, G);
+    DGS_CUDA(cudaMemsetAsync(out_dev, 0, 3 * sizeof(uint64_t), st), "workload memset");
+    launch_workload(p, (const uint2*)(img + I.ranges), (const uint32_t*)(bin + B.point_list),
+                    (const uint32_t*)(img + I.n_contrib), (unsigned long long*)out_dev, st);
+    DGS_CUDA(cudaGetLastError(), "workload");
+    return DGS_OK;
 }
 
 // ---- debug / parity accessors ---------------------------------------------------------

@@ -72,8 +72,9 @@ struct HalvingReduce {
 };
 
 // ---------------------------------------------------------------------------------------
-// tile blending, backward.  grid = (tiles_x, tiles_y, F), 256 threads = 16x16 pixels;
-// a warp covers a 16x2 pixel strip.  grad = AoS float[N][12]:
+// tile blending, backward.  grid = (tiles_x, tiles_y, F), 256 threads = one 16x16 tile; each
+// warp owns an 8x4 pixel rectangle and, like the forward, evaluates only the staged entries
+// whose alpha >= 1/255 footprint can reach that rectangle.  grad = AoS float[N][12]:
 //   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7,8,9 dcolor | 10,11 unused
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __restrict__ grad)
@@ -81,10 +82,11 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
     const FwdParams& f = p.f;
     const int s = blockIdx.z;
     const int tile = blockIdx.y * f.tiles_x + blockIdx.x;
-    const int tid = threadIdx.y * DGS_TILE_X + threadIdx.x;
-    const unsigned lane = tid & 31;
-    const unsigned pixx = blockIdx.x * DGS_TILE_X + threadIdx.x;
-    const unsigned pixy = blockIdx.y * DGS_TILE_Y + threadIdx.y;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    const unsigned wx0 = blockIdx.x * DGS_TILE_X + (warp & 1) * 8, wy0 = blockIdx.y * DGS_TILE_Y + (warp >> 1) * 4;
+    const unsigned pixx = wx0 + (lane & 7), pixy = wy0 + (lane >> 3);
+    const float rx0 = (float)wx0, ry0 = (float)wy0, rx1 = (float)(wx0 + 7), ry1 = (float)(wy0 + 3);
     const bool inside = pixx < (unsigned)f.W && pixy < (unsigned)f.H;
     const size_t HW = (size_t)f.H * f.W;
     const size_t pix_id = (size_t)f.W * pixy + pixx;
@@ -143,7 +145,6 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     const int rounds = (list_len + DGS_TILE_PIX - 1) / DGS_TILE_PIX;
     int todo = list_len;
-    int contributor = list_len;  // index (within the list) of the entry being replayed, +1
     const int my_comp = HalvingReduce<10>::owner(lane);
 
     for (int i = 0; i < rounds; i++, todo -= DGS_TILE_PIX) {
@@ -160,9 +161,18 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
         }
         __syncthreads();
         const int batch = min(DGS_TILE_PIX, todo);
-        for (int j = 0; j < batch; j++) {
-            contributor--;
-            if (contributor >= warp_max) continue;  // warp-uniform
+        // entry j of this batch sits at list position first_pos - j (the batch is staged back to front)
+        const int first_pos = list_len - i * DGS_TILE_PIX - 1;
+        for (int c0 = 0; c0 < batch; c0 += 32) {
+          const int jl = c0 + (int)lane;
+          bool keep = false;
+          if (jl < batch && first_pos - jl < warp_max)
+              keep = entry_reaches_rect(s_xy[jl], s_con[jl], rx0, ry0, rx1, ry1);
+          unsigned mask = __ballot_sync(FULL_MASK, keep);
+          while (mask) {
+            const int j = c0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int contributor = first_pos - j;
             float v[10];
             bool contrib = false;
             float4 con_o;
@@ -216,6 +226,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             }
             const float total = HalvingReduce<10>::run(v, lane);
             if (my_comp >= 0) atomicAdd(grad_s + (size_t)s_id[j] * 12 + my_comp, total);
+          }
         }
     }
 }
@@ -224,7 +235,7 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
-    dim3 grid(f.tiles_x, f.tiles_y, f.F), block(DGS_TILE_X, DGS_TILE_Y);
+    dim3 grid(f.tiles_x, f.tiles_y, f.F), block(DGS_TILE_PIX);
     k_render_bwd<<<grid, block, 0, st>>>(p, reinterpret_cast<float*>(p.g0));
 }
 

@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's camera-motion interface for the hot path.
+
+Mirrors, for curve_type == "se3" (the reference default, arguments/__init__.py:49-74):
+  BezierModel                 scene/bezier.py:20-85       (control points [n, C+1, d])
+  CameraMotionModule.query / get_trajectory / _sample_nu_from_alignment
+                              scene/motion.py:78-178, 209-219
+  MiniCam                     scene/cameras.py:63-74
+  GaussianModel getters       scene/gaussian_model.py:114-137, scene/gaussian_activation.py:29-52
+The sub-frame loop of `query` is replaced by ONE batched render (`renderer.render_blurry`) and the
+pose chain by the on-device generator (`pose.bezier_se3_poses`); names, arguments and the returned
+dictionary keep the reference's meaning. Dataset loading, se3_log initialisation from COLMAP poses,
+save/load and the quaternion curve type are outside the hot path and not provided.
+"""
+import torch
+import torch.nn as nn
+
+from . import renderer
+from .pose import bezier_se3_poses
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))
+
+
+class MiniCam:
+    """Same fields as the reference's MiniCam; camera_center is supplied (it equals the
+    camera-to-world translation) instead of being obtained from a matrix inverse."""
+
+    def __init__(self, width, height, fovy, fovx, znear, zfar, world_view_transform, full_proj_transform,
+                 camera_center=None):
+        self.image_width = width
+        self.image_height = height
+        self.FoVy = fovy
+        self.FoVx = fovx
+        self.znear = znear
+        self.zfar = zfar
+        self.world_view_transform = world_view_transform
+        self.full_proj_transform = full_proj_transform
+        if camera_center is None:
+            camera_center = torch.inverse(world_view_transform)[3][:3]
+        self.camera_center = camera_center
+
+
+class BezierModel(nn.Module):
+    """[n, C+1, d] control points; sample = sum_k binom(C,k) t^(C-k) (1-t)^k ctrl[k]."""
+
+    def __init__(self, initial_points, curve_order, initial_noise=0.001, generator=None):
+        super().__init__()
+        self.curve_order = curve_order
+        pts = initial_points.float()[:, None, :].repeat(1, curve_order + 1, 1)
+        noise = torch.randn(pts.shape, generator=generator).to(pts.device) * initial_noise
+        self._control_points = nn.Parameter((pts + noise).contiguous().requires_grad_(True))
+
+    @property
+    def device(self):
+        return self._control_points.device
+
+    def __len__(self):
+        return self._control_points.shape[0]
+
+
+class GaussianParams:
+    """Minimal stand-in for the reference's GaussianModel on the hot path: raw parameters plus the
+    activations `render` reads (opacity = clamp(.,0,1), scale = exp(.) + lb, rotation = normalize,
+    features = cat(dc, rest))."""
+
+    def __init__(self, xyz, features_dc, features_rest, scaling, rotation, opacity, active_sh_degree,
+                 z_near=0.2, z_far=100.0, use_sigmoid=False, scale_lower_bound=0.0):
+        self._xyz = nn.Parameter(xyz.contiguous())
+        self._features_dc = nn.Parameter(features_dc.contiguous())
+        self._features_rest = nn.Parameter(features_rest.contiguous())
+        self._scaling = nn.Parameter(scaling.contiguous())
+        self._rotation = nn.Parameter(rotation.contiguous())
+        self._opacity = nn.Parameter(opacity.contiguous())
+        self.active_sh_degree = active_sh_degree
+        self.z_near = z_near
+        self.z_far = z_far
+        self.use_sigmoid = use_sigmoid
+        self.scale_lower_bound = scale_lower_bound
+
+    @classmethod
+    def from_scene(cls, scene, **kw):
+        """Build from activated synthetic values (synthetic.Scene): stores log-scales etc."""
+        return cls(scene.means3D.clone(), scene.shs[:, :1, :].clone(), scene.shs[:, 1:, :].clone(),
+                   torch.log(scene.scales), scene.rotations.clone(), scene.opacities.clone(), scene.sh_degree, **kw)
+
+    def parameters(self):
+        return [self._xyz, self._features_dc, self._features_rest, self._scaling, self._rotation, self._opacity]
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_scaling(self):
+        return torch.exp(self._scaling) + self.scale_lower_bound
+
+    @property
+    def get_rotation(self):
+        return torch.nn.functional.normalize(self._rotation)
+
+    @property
+    def get_opacity(self):
+        return self._opacity.clamp(0.0, 1.0)
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+
+class CameraMotionModule:
+    """Per-image Bezier trajectory in se(3) and the blurry-view query.
+
+    cameras: list of reference cameras (need image_width/height, FoVx/FoVy, znear/zfar,
+    projection_matrix [4,4] (already transposed, as in scene/cameras.py:58) and optionally
+    original_image). initial_se3: [n,6] = [log_translation | log_rotation] of each image's c2w.
+    """
+
+    def __init__(self, cameras, initial_se3, curve_order=9, num_subframes=21, curve_random_sample=False,
+                 generator=None):
+        self.curve_order = curve_order
+        self.n_subframes = num_subframes
+        self.curve_type = "se3"
+        self.curve_random_sample = curve_random_sample
+        self.gaussians = None
+        self.original_cam = cameras
+        self._trans = BezierModel(initial_se3[:, :3], curve_order, generator=generator)
+        self._rot = BezierModel(initial_se3[:, 3:], curve_order, generator=generator)
+        n, f = initial_se3.shape[0], num_subframes
+        nu0 = torch.linspace(1 / (f - 1), 1.0 - (1 / (f - 1)), f - 2) if f > 2 else torch.zeros(0)
+        self._nu = nn.Parameter(inverse_sigmoid(nu0)[None, :].repeat(n, 1).to(initial_se3.device).contiguous()
+                                .requires_grad_(True))
+
+    def __len__(self):
+        return len(self._trans)
+
+    @property
+    def device(self):
+        return self._trans.device
+
+    def link_gaussian(self, gaussians):
+        self.gaussians = gaussians
+
+    def parameters(self):
+        return [self._trans._control_points, self._rot._control_points, self._nu]
+
+    def _sample_nu_from_alignment(self, idx):
+        device = self._nu.device
+        nu_mid = torch.sigmoid(self._nu[idx])
+        if self.curve_random_sample:
+            nu_mid = nu_mid + torch.rand_like(nu_mid) / self.n_subframes - (1 / (2 * self.n_subframes))
+        return torch.cat([torch.zeros(1, device=device), nu_mid, torch.ones(1, device=device)]) \
+            .clamp(0.0, 1.0).sort().values
+
+    def get_trajectory_tensors(self, idx, nu=None):
+        """(world_view_transform [F,4,4], full_proj_transform [F,4,4], camera_center [F,3])."""
+        if nu is None:
+            nu = self._sample_nu_from_alignment(idx)
+        ref_cam = self.original_cam[0]
+        return bezier_se3_poses(self._trans._control_points[idx], self._rot._control_points[idx], nu,
+                                ref_cam.projection_matrix)
+
+    def get_trajectory(self, idx, t=None):
+        """List of MiniCam objects, as the reference returns."""
+        view, proj, campos = self.get_trajectory_tensors(idx, t)
+        ref = self.original_cam[0]
+        return [MiniCam(ref.image_width, ref.image_height, ref.FoVy, ref.FoVx, ref.znear, ref.zfar,
+                        view[i], proj[i], campos[i]) for i in range(view.shape[0])]
+
+    def get_gt_image(self, idx):
+        return getattr(self.original_cam[idx], "original_image", None)
+
+    def query(self, cam_idx, subframe_indice="all", post_process=None, background="random"):
+        """Render a blurry view. Same arguments and returned keys as the reference
+        (scene/motion.py:78-160): 'blurred', 'gt', 'subframes', 'depths', 'render_pkgs'."""
+        assert self.gaussians is not None
+        gaussians = self.gaussians
+        if isinstance(background, str) and background == "random":
+            bg = torch.rand(3, device=gaussians.get_xyz.device)
+        else:
+            bg = background
+
+        if isinstance(subframe_indice, str) and subframe_indice == "all":
+            nu = None
+        else:
+            nu = self._sample_nu_from_alignment(cam_idx)
+            if isinstance(subframe_indice, int):
+                subfr_idx = torch.linspace(0, nu.shape[0] - 1, subframe_indice, device=nu.device).long()
+            else:
+                subfr_idx = subframe_indice
+            nu = nu[subfr_idx]
+        view, proj, campos = self.get_trajectory_tensors(cam_idx, nu)
+        pkg = renderer.render_blurry(view, proj, campos, self.original_cam[0], gaussians, bg)
+
+        blurred = pkg["blurred"]
+        if post_process is not None:
+            blurred = post_process(blurred)
+        F = view.shape[0]
+        render_pkgs = [{"render": pkg["render"][s], "depth": pkg["depth"][s],
+                        "viewspace_points": pkg["viewspace_points"], "viewspace_index": s,
+                        "visibility_filter": pkg["visibility_filter"][s], "radii": pkg["radii"][s]}
+                       for s in range(F)]
+        return {"blurred": blurred, "gt": self.get_gt_image(cam_idx), "subframes": pkg["render"],
+                "depths": pkg["depth"], "render_pkgs": render_pkgs, "batched": pkg}

@@ -120,16 +120,19 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
     has_colors = colors_precomp is not None and colors_precomp.numel() != 0
     has_scales = scales is not None and scales.numel() != 0
     has_cov = cov3Ds_precomp is not None and cov3Ds_precomp.numel() != 0
-    dmeans2D = torch.empty((F, P, 3), **f32) if want_means2D else None
-    dmeans3D = torch.zeros((P, 3), **f32)
-    dsh = torch.zeros((P, M, 3), **f32) if has_sh else torch.zeros((P, 0, 3), **f32)
-    dopacity = torch.zeros((P, 1), **f32)
-    dscales = torch.zeros((P, 3), **f32) if has_scales else None
-    drot = torch.zeros((P, 4), **f32) if has_scales else None
-    dcolors = torch.zeros((P, 3), **f32) if has_colors else None
-    dcov = torch.zeros((P, 6), **f32) if has_cov else None
-    dview = torch.zeros((F, 4, 4), **f32)
-    dproj = torch.zeros((F, 4, 4), **f32)
+    # every output below is fully written by the kernels (no zero-fill needed, unlike the reference's
+    # 12 torch::zeros per sub-frame, rasterize_points.cu:163-175)
+    alloc = torch.zeros if (P == 0 or F == 0) else torch.empty
+    dmeans2D = alloc((F, P, 3), **f32) if want_means2D else None
+    dmeans3D = alloc((P, 3), **f32)
+    dsh = alloc((P, M, 3), **f32) if has_sh else torch.zeros((P, 0, 3), **f32)
+    dopacity = alloc((P, 1), **f32)
+    dscales = alloc((P, 3), **f32) if has_scales else None
+    drot = alloc((P, 4), **f32) if has_scales else None
+    dcolors = alloc((P, 3), **f32) if has_colors else None
+    dcov = alloc((P, 6), **f32) if has_cov else None
+    dview = alloc((F, 4, 4), **f32)
+    dproj = alloc((F, 4, 4), **f32)
     if P == 0 or F == 0:
         return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj
     scratch = torch.empty(int(lib.dgs_blur_backward_scratch_bytes(P, F)), dtype=torch.uint8, device=dev)

@@ -168,6 +168,24 @@ int dgs_debug_image(const char* image_buffer, int F, int width, int height,
 int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bits);
 
 /*
+ * Measurement hooks (used by bench.py; no effect on results).
+ * dgs_profile_enable(1): every stage of the calls above is bracketed by a CUDA event pair on the
+ * caller's stream.  dgs_profile_read synchronises those events and returns accumulated milliseconds
+ * and call counts per stage (names from dgs_profile_stage_name).  dgs_launch_count = number of
+ * kernels of THIS library launched so far (library scan/sort kernels are not counted).
+ * dgs_debug_workload replays the compositing loop and writes {E, K, E_b} (list entries
+ * evaluated, entries that contributed, entries replayed by the backward) to out_dev[3] (device).
+ */
+int dgs_profile_enable(int on);
+int dgs_profile_num_stages(void);
+const char* dgs_profile_stage_name(int i);
+int dgs_profile_read(double* ms, int64_t* calls, int n, int reset);
+int64_t dgs_launch_count(int reset);
+int dgs_debug_workload(const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                       int P, int F, int width, int height, int64_t num_rendered, uint64_t* out_dev,
+                       void* stream);
+
+/*
  * Sub-frame poses from Bezier control points in se(3) (curve_type == "se3").
  *   ctrl_trans, ctrl_rot [C+1,3] fp32 (control point k weighted by binom(C,k) t^(C-k) (1-t)^k)
  *   nu [F] fp32 in [0,1];  proj_t [16] = the reference camera's `projection_matrix`
