@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing for the blurry-view path: one process per GPU, torch.distributed (NCCL over
+NVLink/NVSwitch on the GPU box; gloo in the CPU tests).
+
+The reference is single-GPU; the path shards along its two independent axes:
+  * views of a batch   -> each rank renders whole blurry views; the Gaussian gradients are summed with
+                          one all-reduce of a flat buffer (`FlatGradBuffer`) -- weak scaling;
+  * sub-frames of a view -> each rank renders a contiguous block of the F sub-frames
+                          (`subframe_shard`), the partial blurry images are summed (`all_reduce_sum`,
+                          identity backward) and the gradients all-reduced as above -- strong scaling.
+No collective sits inside the rasterizer itself.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def subframe_shard(num_subframes, rank, world_size):
+    """Contiguous block [start, stop) of sub-frames for `rank`; blocks differ by at most one sub-frame
+    and keep temporal neighbours on the same rank (except at block edges)."""
+    base, rem = divmod(num_subframes, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """y = sum over ranks of x. Every rank then evaluates the SAME loss on y, so dL/dx_r = dL/dy: the
+    backward is the identity (the per-rank parameter gradients are summed later by FlatGradBuffer)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = x.contiguous().clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def all_reduce_sum(x):
+    return _AllReduceSum.apply(x)
+
+
+class FlatGradBuffer:
+    """One flat fp32 gradient buffer; each parameter's .grad is a view into it, so the whole set of
+    Gaussian gradients (P*(11+3M) floats) moves with a single all-reduce."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return self.flat
+
+
+def render_blurry_sharded(cmm, cam_idx, background, nu=None):
+    """Sub-frame-sharded blurry view: this rank renders its block of the F sub-frames of image
+    `cam_idx`; returns (blurred [3,H,W] identical on every rank, local package, (start, stop))."""
+    from . import renderer
+    rank, ws = world()
+    view, proj, campos = cmm.get_trajectory_tensors(cam_idx, nu)
+    F = view.shape[0]
+    a, b = subframe_shard(F, rank, ws)
+    pkg = renderer.render_blurry(view[a:b].contiguous(), proj[a:b].contiguous(), campos[a:b].contiguous(),
+                                 cmm.original_cam[0], cmm.gaussians, background, blur_denominator=float(F))
+    return all_reduce_sum(pkg["blurred"]), pkg, (a, b)

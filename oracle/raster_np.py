@@ -80,9 +80,14 @@ def cov3d(scales, rots, mod):
     def p2(a, b, c, d, sign):  # 2*(a*b +- c*d)
         return (two * fma(a, b, (sign * (c * d)).astype(f32))).astype(f32)
 
-    R = [[m1(y, y, zz, zz), p2(x, y, r, zz, f32(-1)), p2(x, zz, r, y, f32(1))],
+    # Which product of each `a*b +- c*d` gets fused depends on how nvcc shares the products between
+    # the nine entries (read off the reference's sm_100 SASS): y*y + z*z is a plain add of two rounded
+    # products; x*z +- r*y fuses r*y; the others fuse their first product.
+    yy_zz = ((y * y).astype(f32) + (zz * zz).astype(f32)).astype(f32)
+    xz = (x * zz).astype(f32)
+    R = [[(one - two * yy_zz).astype(f32), p2(x, y, r, zz, f32(-1)), (two * fma(r, y, xz)).astype(f32)],
          [p2(x, y, r, zz, f32(1)), m1(x, x, zz, zz), p2(y, zz, r, x, f32(-1))],
-         [p2(x, zz, r, y, f32(-1)), p2(y, zz, r, x, f32(1)), m1(x, x, y, y)]]
+         [(two * fma(-r, y, xz)).astype(f32), p2(y, zz, r, x, f32(1)), m1(x, x, y, y)]]
     S = [[s[0], z, z], [z, s[1], z], [z, z, s[2]]]
     M = mat3_mul(S, R)
     Sigma = mat3_mul(mat3_t(M), M)

@@ -1,0 +1,385 @@
+"""GPU parity tests (pytest -m gpu): libdgs_b200 through its C-ABI binding against
+  (1) the reference's own CUDA rasterizer / simple-knn (oracle/_ref, compiled from the reference sources),
+  (2) the committed golden vectors (tests/golden/, produced by (1) / by the reference's Python),
+  (3) the CPU restatement (oracle/raster_np.py, oracle/pose_torch.py),
+and size-independent properties at BASELINE.json's full c2 size.
+
+Bars: tile keys / ranges / sorted lists / radii / n_contrib bit-exact; images max-abs <= 1e-4 (fp32);
+gradients <= 1e-3 relative (max-abs error over the tensor's max-abs; the reference's own float atomics
+give ~1e-4 run-to-run).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_utils as pu
+from deblurgs_b200 import _lib, synthetic
+from oracle import ref_cuda
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref not built")
+
+
+def relmax(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def test_native_library_is_the_thing_running():
+    lib = _lib.load()
+    assert lib.dgs_compiled_arch() == 1000
+    assert torch.cuda.get_device_capability()[0] == 10
+    before = lib.dgs_launch_count(0)
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    pu.ours_forward(cam, scene, bg, view, proj, campos)
+    assert lib.dgs_launch_count(0) - before >= 5
+
+
+def _compare_forward(name, sh_degree=3, use_sigmoid=False, P=None, F=None):
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs(name, sh_degree=3, P=P, F=F)
+    P, F, W, H = scene.means3D.shape[0], view.shape[0], cam.width, cam.height
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos, sh_degree=sh_degree, use_sigmoid=use_sigmoid)
+    dec = pu.ours_decode(fw, P, F, W, H)
+    tb = dec["tile_bits"]
+    base, refs = 0, []
+    for s in range(F):
+        r = ref_cuda.forward(scene.means3D, scene.shs, None, scene.opacities, scene.scales, scene.rotations, None,
+                             view[s].contiguous(), proj[s].contiguous(), campos[s].contiguous(), bg, W, H,
+                             cam.tanfovx, cam.tanfovy, sh_degree, use_sigmoid=use_sigmoid)
+        refs.append(r)
+        vis = r["radii"] > 0
+        assert torch.equal(r["radii"], fw["radii"][s])
+        assert torch.equal(r["geom"]["tiles_touched"], dec["tiles_touched"][s])
+        assert torch.equal(r["geom"]["depths"].view(torch.int32)[vis], dec["depths"][s].view(torch.int32)[vis])
+        assert torch.equal(r["geom"]["means2D"].view(P, 2)[vis], dec["means2D"][s][vis])
+        assert torch.equal(r["geom"]["conic_opacity"].view(P, 4)[vis], dec["conic_opacity"][s][vis])
+        assert (r["geom"]["rgb"].view(P, 3)[vis] - dec["rgb"][s][vis]).abs().max() <= 1e-6
+        R = r["num_rendered"]
+        keys = dec["keys"][base:base + R]
+        assert torch.equal(keys & ((1 << (32 + tb)) - 1), r["binning"]["point_list_keys"])   # low bits = reference key
+        assert bool(((keys >> (32 + tb)) == s).all())                                           # high bits = sub-frame
+        assert torch.equal(dec["point_list"][base:base + R], r["binning"]["point_list"])
+        mine = dec["ranges"][s].clone()
+        nz = mine[:, 1] > mine[:, 0]
+        mine[nz] -= base
+        assert torch.equal(mine, r["image"]["ranges"][:2 * tiles].view(tiles, 2))
+        assert torch.equal(r["image"]["n_contrib"].view(H, W), dec["n_contrib"][s])
+        assert (r["image"]["accum_alpha"].view(H, W) - dec["final_T"][s]).abs().max() <= 1e-6
+        assert (r["color"] - fw["color"][s]).abs().max() <= 1e-4
+        assert (r["depth"] - fw["depth"][s]).abs().max() <= 1e-4 * 100
+        base += R
+    assert base == fw["num_rendered"]
+    blur = torch.stack([r["color"] for r in refs]).mean(0)
+    assert (blur - fw["blur"]).abs().max() <= 1e-4
+    return cam, scene, bg, view, proj, campos, fw, refs
+
+
+@needs_ref
+@pytest.mark.parametrize("name,deg,sig", [("tiny", 3, False), ("tiny", 0, False), ("tiny", 1, False), ("tiny", 2, False),
+                                          ("tiny", 3, True), ("small", 3, False), ("c1", 3, False)])
+def test_forward_bit_exact_vs_reference_cuda(name, deg, sig):
+    _compare_forward(name, sh_degree=deg, use_sigmoid=sig)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,sig", [("tiny", False), ("tiny", True), ("small", False), ("c1", False)])
+def test_backward_vs_reference_cuda(name, sig):
+    cam, scene, bg, view, proj, campos, fw, refs = _compare_forward(name, use_sigmoid=sig)
+    F, W, H = view.shape[0], cam.width, cam.height
+    g = torch.Generator().manual_seed(7)
+    dpix = (torch.randn(F, 3, H, W, generator=g) / (3 * H * W)).cuda()
+    ddep = (torch.randn(F, 1, H, W, generator=g) / (H * W) * 0.1).cuda()
+    mine = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix, ddep, use_sigmoid=sig)
+    acc, per = None, []
+    for s in range(F):
+        b = ref_cuda.backward(refs[s], scene.means3D, scene.shs, None, scene.scales, scene.rotations, None,
+                              view[s].contiguous(), proj[s].contiguous(), campos[s].contiguous(), bg, W, H,
+                              cam.tanfovx, cam.tanfovy, 3, dpix[s].contiguous(), ddep[s].contiguous(), use_sigmoid=sig)
+        per.append(b)
+        acc = {k: v.double().clone() for k, v in b.items()} if acc is None else {k: acc[k] + v.double() for k, v in b.items()}
+    for k in ["dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"]:
+        assert relmax(mine[k], acc[k]) <= 1e-3, k
+    assert relmax(mine["dL_dviewmatrix"], torch.stack([b["dL_dviewmatrix"] for b in per])) <= 1e-3
+    assert relmax(mine["dL_dprojmatrix"], torch.stack([b["dL_dprojmatrix"] for b in per])) <= 1e-3
+    assert relmax(mine["dL_dmeans2D"], torch.stack([b["dL_dmeans2D"] for b in per])) <= 1e-3
+    # culled Gaussians get exactly zero gradient (backward.cu:158,393)
+    dead = (fw["radii"] <= 0).all(dim=0)
+    assert float(mine["dL_dmeans3D"][dead].abs().max() if dead.any() else 0.0) == 0.0
+
+
+@needs_ref
+def test_precomputed_colors_and_covariance_and_scale_modifier():
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    P, F, W, H = scene.means3D.shape[0], view.shape[0], cam.width, cam.height
+    g = torch.Generator().manual_seed(3)
+    colors = torch.rand(P, 3, generator=g).cuda()
+    # covariance from the library's own geometry of a scales/rotations run is not exposed; build it in torch
+    q = scene.rotations
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                      2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                      2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(P, 3, 3)
+    L = Rm * scene.scales[:, None, :]
+    Sg = L @ L.transpose(1, 2)
+    cov = torch.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1).contiguous()
+    dpix = (torch.randn(F, 3, H, W, generator=g) / (3 * H * W)).cuda()
+    ddep = torch.zeros(F, 1, H, W).cuda()
+    for kw in [dict(colors_precomp=colors), dict(cov3D_precomp=cov), dict(scale_modifier=0.7)]:
+        fw = pu.ours_forward(cam, scene, bg, view, proj, campos, **kw)
+        mine = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix, ddep, **kw)
+        cp, cv, mod = kw.get("colors_precomp"), kw.get("cov3D_precomp"), kw.get("scale_modifier", 1.0)
+        acc = None
+        for s in range(F):
+            r = ref_cuda.forward(scene.means3D, None if cp is not None else scene.shs, cp, scene.opacities,
+                                 None if cv is not None else scene.scales, None if cv is not None else scene.rotations,
+                                 cv, view[s].contiguous(), proj[s].contiguous(), campos[s].contiguous(), bg, W, H,
+                                 cam.tanfovx, cam.tanfovy, 3, scale_modifier=mod)
+            assert torch.equal(r["radii"], fw["radii"][s])
+            assert (r["color"] - fw["color"][s]).abs().max() <= 1e-4
+            b = ref_cuda.backward(r, scene.means3D, None if cp is not None else scene.shs, cp,
+                                  None if cv is not None else scene.scales, None if cv is not None else scene.rotations,
+                                  cv, view[s].contiguous(), proj[s].contiguous(), campos[s].contiguous(), bg, W, H,
+                                  cam.tanfovx, cam.tanfovy, 3, dpix[s].contiguous(), ddep[s].contiguous(),
+                                  scale_modifier=mod)
+            acc = {k: v.double().clone() for k, v in b.items()} if acc is None else {k: acc[k] + v.double() for k, v in b.items()}
+        assert relmax(mine["dL_dmeans3D"], acc["dL_dmeans3D"]) <= 1e-3
+        if cp is not None:
+            assert relmax(mine["dL_dcolors"], acc["dL_dcolors"]) <= 1e-3
+        if cv is not None:
+            assert relmax(mine["dL_dcov3D"], acc["dL_dcov3D"]) <= 1e-3
+        else:
+            assert relmax(mine["dL_dscales"], acc["dL_dscales"]) <= 1e-3
+            assert relmax(mine["dL_drotations"], acc["dL_drotations"]) <= 1e-3
+
+
+@pytest.mark.parametrize("tag,sig", [("tiny", False), ("tiny_sigmoid", True)])
+def test_against_committed_golden_vectors(tag, sig):
+    """No oracle/_ref needed: the golden file holds the reference CUDA extension's outputs."""
+    g = np.load(os.path.join(GOLD, "raster_golden_%s.npz" % tag))
+    P, W, H, F, order = synthetic.CONFIGS["tiny"]
+    cam = synthetic.make_camera(W, H)
+    scene = synthetic.make_scene(P, cam).to("cuda")
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    view, proj, campos, bg = t("view"), t("proj"), t("campos"), t("bg")
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos, use_sigmoid=sig)
+    dec = pu.ours_decode(fw, P, F, W, H)
+    tb, base = dec["tile_bits"], 0
+    for s in range(F):
+        k = "s%d_" % s
+        assert torch.equal(fw["radii"][s], t(k + "radii"))
+        R = int(g[k + "num_rendered"])
+        assert torch.equal(dec["keys"][base:base + R] & ((1 << (32 + tb)) - 1), t(k + "keys"))
+        assert torch.equal(dec["point_list"][base:base + R], t(k + "point_list"))
+        assert torch.equal(dec["n_contrib"][s].flatten(), t(k + "n_contrib"))
+        assert (fw["color"][s] - t(k + "color")).abs().max() <= 1e-4
+        assert (fw["depth"][s] - t(k + "depth")).abs().max() <= 1e-2
+        base += R
+    mine = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, t("dL_dpix"), t("dL_ddepth"), use_sigmoid=sig)
+    for name in ["dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"]:
+        ref = sum(torch.from_numpy(g["s%d_%s" % (s, name)]).double() for s in range(F)).cuda()
+        assert relmax(mine[name], ref.view_as(mine[name])) <= 1e-3, name
+    for name in ["dL_dviewmatrix", "dL_dprojmatrix"]:
+        ref = torch.stack([torch.from_numpy(g["s%d_%s" % (s, name)]) for s in range(F)]).cuda()
+        assert relmax(mine[name], ref) <= 1e-3, name
+
+
+def test_against_cpu_oracle():
+    from oracle import raster_np as rn
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    P, F, W, H = scene.means3D.shape[0], view.shape[0], cam.width, cam.height
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos)
+    dec = pu.ours_decode(fw, P, F, W, H)
+    a = [t.cpu().numpy() for t in (scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs)]
+    g = torch.Generator().manual_seed(5)
+    dpix = torch.randn(F, 3, H, W, generator=g) / (3 * H * W)
+    ddep = torch.randn(F, 1, H, W, generator=g) / (H * W) * 0.1
+    mine = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix.cuda(), ddep.cuda())
+    gm = 0
+    base = 0
+    for s in range(F):
+        o = rn.forward(a[0], a[1], a[2], a[3], a[4], 3, view[s].cpu().numpy(), proj[s].cpu().numpy(),
+                       campos[s].cpu().numpy(), bg.cpu().numpy(), W, H, cam.tanfovx, cam.tanfovy)
+        assert np.array_equal(o["pre"]["radii"], fw["radii"][s].cpu().numpy())
+        R = o["point_list"].size
+        assert np.array_equal(o["point_list"].astype(np.int32), dec["point_list"][base:base + R].cpu().numpy())
+        base += R
+        err = np.abs(o["color"] - fw["color"][s].cpu().numpy())
+        assert np.quantile(err, 0.999) < 1e-4 and err.max() < 2e-2     # CPU exp != CUDA expf: isolated flips
+        b = rn.backward(o, a[0], a[1], a[2], a[4], 3, view[s].cpu().numpy(), proj[s].cpu().numpy(),
+                        campos[s].cpu().numpy(), bg.cpu().numpy(), W, H, cam.tanfovx, cam.tanfovy,
+                        dpix[s].numpy(), ddep[s].numpy())
+        gm = gm + b["dL_dmeans3D"]
+        assert relmax(mine["dL_dviewmatrix"][s].cpu(), torch.from_numpy(b["dL_dviewmatrix"])) < 2e-3
+        assert relmax(mine["dL_dprojmatrix"][s].cpu(), torch.from_numpy(b["dL_dprojmatrix"])) < 2e-3
+    assert relmax(mine["dL_dmeans3D"].cpu(), torch.from_numpy(gm)) < 2e-3
+
+
+def test_edge_cases():
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    F, W, H = view.shape[0], cam.width, cam.height
+    # P == 0: zero images (rasterize_points.cu:85)
+    empty = synthetic.Scene(scene.means3D[:0], scene.scales[:0], scene.rotations[:0], scene.opacities[:0],
+                            scene.shs[:0], 3)
+    fw = pu.ours_forward(cam, empty, bg, view, proj, campos)
+    assert fw["num_rendered"] == 0 and float(fw["color"].abs().max()) == 0.0
+    # everything culled (behind the camera): num_rendered == 0 -> bg, z_far, T=1, n_contrib=0
+    far = synthetic.Scene(scene.means3D - 100.0 * torch.tensor([0.0, 0.0, 1.0], device="cuda"), scene.scales,
+                          scene.rotations, scene.opacities, scene.shs, 3)
+    fw = pu.ours_forward(cam, far, bg, view, proj, campos)
+    dec = pu.ours_decode(fw, far.means3D.shape[0], F, W, H)
+    if fw["num_rendered"] == 0:
+        assert torch.allclose(fw["color"], bg.view(1, 3, 1, 1).expand_as(fw["color"]))
+        assert torch.allclose(fw["depth"], torch.full_like(fw["depth"], 100.0))
+        assert bool((dec["n_contrib"] == 0).all()) and bool((dec["final_T"] == 1).all())
+        mine = pu.ours_backward(cam, far, bg, view, proj, campos, fw, torch.ones(F, 3, H, W).cuda(),
+                                torch.ones(F, 1, H, W).cuda())
+        assert float(mine["dL_dmeans3D"].abs().max()) == 0.0 and float(mine["dL_dviewmatrix"].abs().max()) == 0.0
+    # image size not a multiple of the tile size; single sub-frame
+    cam2 = synthetic.make_camera(75, 37)
+    sc2 = synthetic.make_scene(500, cam2).to("cuda")
+    v1, p1, c1 = view[:1].contiguous(), proj[:1].contiguous(), campos[:1].contiguous()
+    fw = pu.ours_forward(cam2, sc2, bg, v1, p1, c1)
+    assert fw["color"].shape == (1, 3, 37, 75) and torch.isfinite(fw["color"]).all()
+    if ref_cuda.available():
+        r = ref_cuda.forward(sc2.means3D, sc2.shs, None, sc2.opacities, sc2.scales, sc2.rotations, None,
+                             v1[0].contiguous(), p1[0].contiguous(), c1[0].contiguous(), bg, 75, 37, cam2.tanfovx,
+                             cam2.tanfovy, 3)
+        assert torch.equal(r["radii"], fw["radii"][0]) and (r["color"] - fw["color"][0]).abs().max() <= 1e-4
+
+
+def test_batching_invariance_and_determinism():
+    """F sub-frames in one batched call == F single-view calls, bit for bit; forward is deterministic."""
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("small")
+    F = view.shape[0]
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos)
+    fw2 = pu.ours_forward(cam, scene, bg, view, proj, campos)
+    assert torch.equal(fw["color"], fw2["color"]) and torch.equal(fw["radii"], fw2["radii"])
+    tot = 0
+    for s in range(F):
+        one = pu.ours_forward(cam, scene, bg, view[s:s + 1].contiguous(), proj[s:s + 1].contiguous(),
+                              campos[s:s + 1].contiguous())
+        assert torch.equal(one["color"][0], fw["color"][s]) and torch.equal(one["depth"][0], fw["depth"][s])
+        assert torch.equal(one["radii"][0], fw["radii"][s])
+        tot += one["num_rendered"]
+    assert tot == fw["num_rendered"]
+
+
+@pytest.mark.parametrize("tag", ["c3f4", "c9f16", "c9f21", "c1f3", "small_rot"])
+def test_pose_kernel_vs_reference_python_golden(tag):
+    from deblurgs_b200.pose import bezier_se3_poses
+    c = torch.load(os.path.join(GOLD, "pose_golden.pt"))[tag]
+    ct = c["ctrl_trans"].cuda().requires_grad_(True)
+    cr = c["ctrl_rot"].cuda().requires_grad_(True)
+    nu = c["nu"].cuda().requires_grad_(True)
+    view, proj, center = bezier_se3_poses(ct, cr, nu, c["proj_t"].cuda())
+
+    def ulp_close(a, b, n=2):
+        a, b = a.cpu(), b.cpu()
+        tol = n * torch.finfo(torch.float32).eps * b.abs().clamp_min(1e-3)
+        return bool(((a - b).abs() <= tol).all())
+    assert ulp_close(view, c["view"]) and ulp_close(proj, c["proj"], 4)
+    assert (center.cpu() - c["center"]).abs().max() <= 1e-6      # reference: fp32 matrix inverse
+    loss = (view * c["w_view"].cuda()).sum() + (proj * c["w_proj"].cuda()).sum()
+    gt, gr, gn = torch.autograd.grad(loss, [ct, cr, nu])
+    assert relmax(gt.cpu(), c["g_ctrl_trans"]) <= 1e-3 and relmax(gr.cpu(), c["g_ctrl_rot"]) <= 1e-3
+    # dL/dnu: compare after the reference's sigmoid/sort chain on the interior points (ends are constants)
+    nu_p = c["nu_param"].clone().requires_grad_(True)
+    from oracle import pose_torch as pt
+    (pt.sample_nu(nu_p, c["F"]) * gn.cpu()).sum().backward()
+    assert relmax(nu_p.grad, c["g_nu_param"]) <= 1e-3
+
+
+@needs_ref
+@pytest.mark.parametrize("P", [5, 1000, 50_000])
+def test_knn_matches_reference(P):
+    from deblurgs_b200 import distCUDA2
+    g = torch.Generator().manual_seed(P)
+    pts = (torch.randn(P, 3, generator=g) * torch.tensor([3.0, 1.0, 0.3])).cuda()
+    mine = distCUDA2(pts)
+    ref = ref_cuda.knn(pts)
+    assert torch.equal(mine, ref)
+    if P <= 1000:
+        d = torch.cdist(pts.double(), pts.double()) ** 2
+        d.fill_diagonal_(float("inf"))
+        brute = d.topk(3, dim=1, largest=False).values.mean(1)
+        assert torch.allclose(mine.double(), brute, rtol=1e-5)
+
+
+def test_drop_in_module_against_reference_extension():
+    """GaussianRasterizer (single view, autograd) against the reference's installed extension, if present."""
+    ref_dir = os.path.join(pu.ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "diff_gaussian_rasterization")):
+        pytest.skip("baseline/_ref not installed")
+    sys.path.insert(0, ref_dir)
+    import diff_gaussian_rasterization as ref_mod
+    import deblurgs_b200 as dg
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    W, H = cam.width, cam.height
+    g = torch.Generator().manual_seed(1)
+    wimg, wdep = torch.randn(3, H, W, generator=g).cuda(), torch.randn(1, H, W, generator=g).cuda() * 0.01
+    outs = []
+    for mod in (dg, ref_mod):
+        leaves = [t.clone().requires_grad_(True) for t in (scene.means3D, scene.shs, scene.opacities, scene.scales,
+                                                           scene.rotations, view[1], proj[1])]
+        m3, sh, op, sc, ro, vm, pm = leaves
+        m2 = torch.zeros_like(m3, requires_grad=True)
+        rs = mod.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, 0.2, 100.0, False, 3,
+                                               campos[1], False, False)
+        img, dep, radii = mod.GaussianRasterizer(rs)(means3D=m3, means2D=m2, shs=sh, opacities=op, scales=sc,
+                                                     rotations=ro, viewmatrix=vm, projmatrix=pm)
+        ((img * wimg).sum() + (dep * wdep).sum()).backward()
+        outs.append((img.detach(), dep.detach(), radii, [t.grad for t in leaves] + [m2.grad]))
+    (i0, d0, r0, g0), (i1, d1, r1, g1) = outs
+    assert torch.equal(r0, r1) and (i0 - i1).abs().max() <= 1e-4 and (d0 - d1).abs().max() <= 1e-2
+    for a, b in zip(g0, g1):
+        assert a.shape == b.shape and relmax(a, b) <= 1e-3
+
+
+def test_full_size_properties_c2():
+    """BASELINE config c2 (300k Gaussians, 600x400, F=16): properties that need no oracle."""
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("c2")
+    P, F, W, H = scene.means3D.shape[0], view.shape[0], cam.width, cam.height
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos)
+    dec = pu.ours_decode(fw, P, F, W, H)
+    D = fw["num_rendered"]
+    tb = dec["tile_bits"]
+    keys = dec["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                                 # sortedness
+    assert int(dec["tiles_touched"].sum()) == D                                # checksum of counts
+    assert int(dec["point_offsets"].view(-1)[-1]) == D                         # scan total
+    tile_of = ((keys >> 32) & ((1 << tb) - 1)) + (keys >> (32 + tb)) * dec["ranges"].shape[1]
+    rng = dec["ranges"].view(-1, 2).long()
+    lens = (rng[:, 1] - rng[:, 0])
+    assert int(lens.sum()) == D                                                # ranges partition the list
+    cnt = torch.bincount(tile_of, minlength=rng.shape[0])
+    assert torch.equal(cnt, lens)
+    # depth bits along each tile list are non-decreasing (front-to-back)
+    same = tile_of[1:] == tile_of[:-1]
+    assert bool(((keys[1:] & 0xffffffff) >= (keys[:-1] & 0xffffffff))[same].all())
+    # every list entry refers to a Gaussian that is visible in that sub-frame
+    sf = (keys >> (32 + tb))
+    assert bool((fw["radii"][sf, dec["point_list"].long()] > 0).all())
+    # blurred image = mean of the sub-frames; transmittance in [0,1]; n_contrib within the tile list
+    assert (fw["blur"] - fw["color"].mean(0)).abs().max() <= 1e-5
+    assert float(dec["final_T"].min()) >= 0 and float(dec["final_T"].max()) <= 1
+    # linearity of the backward in the incoming gradient
+    g = torch.Generator().manual_seed(0)
+    d1 = (torch.randn(F, 3, H, W, generator=g) / (H * W)).cuda()
+    z = torch.zeros(F, 1, H, W).cuda()
+    b1 = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, d1, z)
+    b2 = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, 2 * d1, z)
+    for k in ["dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dviewmatrix", "dL_dprojmatrix"]:
+        assert relmax(b2[k], 2 * b1[k]) <= 1e-3, k
+    # a constant colour shift of the target does not move geometry: zero incoming gradient -> zero gradients
+    b0 = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, torch.zeros_like(d1), z)
+    assert float(b0["dL_dmeans3D"].abs().max()) == 0.0 and float(b0["dL_dsh"].abs().max()) == 0.0
+
+
+def test_public_api_blurry_query_and_smoke():
+    import __graft_entry__ as ge
+    ge.smoke()

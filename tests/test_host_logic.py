@@ -1,0 +1,80 @@
+"""CPU: host-side mirror of the reference interface (argument checking, settings layout, nu sampling,
+signature tolerance) -- no device work."""
+import inspect
+
+import pytest
+import torch
+
+import deblurgs_b200 as dg
+from deblurgs_b200 import motion, renderer
+from oracle import pose_torch as pt
+
+
+def test_settings_fields_match_reference_order():
+    # DGR/diff_gaussian_rasterization/__init__.py:172-187
+    assert dg.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "z_near", "z_far",
+        "use_sigmoid", "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_rasterizer_forward_signature_and_errors():
+    sig = inspect.signature(dg.GaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                        "rotations", "cov3D_precomp", "viewmatrix", "projmatrix"]
+    rs = dg.GaussianRasterizationSettings(8, 8, 1.0, 1.0, torch.zeros(3), 1.0, 0.2, 100.0, False, 0, torch.zeros(3),
+                                          False, False)
+    r = dg.GaussianRasterizer(rs)
+    z = torch.zeros(2, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=z, means2D=z, opacities=z[:, :1], scales=z, rotations=torch.zeros(2, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=z, means2D=z, opacities=z[:, :1], shs=torch.zeros(2, 1, 3), colors_precomp=z, scales=z,
+          rotations=torch.zeros(2, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=z, means2D=z, opacities=z[:, :1], shs=torch.zeros(2, 1, 3))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=z, means2D=z, opacities=z[:, :1], shs=torch.zeros(2, 1, 3), scales=z, rotations=torch.zeros(2, 4),
+          cov3D_precomp=torch.zeros(2, 6))
+
+
+def test_render_signature_is_the_reference_one():
+    # gaussian_renderer/__init__.py:18
+    names = list(inspect.signature(renderer.render).parameters)
+    assert names[:5] == ["viewpoint_camera", "pc", "bg_color", "scaling_modifier", "override_color"]
+
+
+def test_nu_sampling_matches_oracle():
+    class Cam:
+        image_width, image_height, FoVx, FoVy, znear, zfar = 8, 8, 1.0, 1.0, 0.01, 100.0
+        projection_matrix = torch.eye(4)
+    for F in (3, 4, 16, 21):
+        cmm = motion.CameraMotionModule([Cam], torch.zeros(2, 6), curve_order=3, num_subframes=F)
+        assert cmm._nu.shape == (2, F - 2)
+        nu = cmm._sample_nu_from_alignment(1)
+        assert torch.equal(nu.detach(), pt.sample_nu(cmm._nu[1].detach(), F))
+        assert nu[0] == 0 and nu[-1] == 1 and torch.all(nu[1:] >= nu[:-1])
+        # reference init: linspace(0,1,F) (scene/motion.py:55)
+        assert torch.allclose(nu.detach(), torch.linspace(0, 1, F), atol=1e-6)
+
+
+def test_gaussian_params_activations():
+    from deblurgs_b200 import synthetic
+    cam = synthetic.make_camera(64, 48)
+    sc = synthetic.make_scene(50, cam)
+    g = motion.GaussianParams.from_scene(sc)
+    assert torch.allclose(g.get_scaling, sc.scales, rtol=1e-6)
+    assert torch.allclose(g.get_rotation.norm(dim=1), torch.ones(50), atol=1e-6)
+    assert g.get_features.shape == (50, 16, 3) and torch.equal(g.get_features, sc.shs)
+    g._opacity.data[0] = 1.7
+    g._opacity.data[1] = -0.2
+    assert g.get_opacity[0] == 1.0 and g.get_opacity[1] == 0.0     # Clamp, not sigmoid
+
+
+def test_synthetic_scene_is_deterministic_and_mostly_visible():
+    from deblurgs_b200 import synthetic
+    cam = synthetic.make_camera(600, 400)
+    a, b = synthetic.make_scene(1000, cam), synthetic.make_scene(1000, cam)
+    assert torch.equal(a.means3D, b.means3D) and torch.equal(a.shs, b.shs)
+    assert abs(cam.tanfovx - 600 / (2 * 1.2 * 600)) < 1e-12
+    t = synthetic.make_trajectory(16, 9)
+    assert t.ctrl_trans.shape == (10, 3) and torch.equal(t.nu, torch.linspace(0, 1, 16))
