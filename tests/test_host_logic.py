@@ -78,3 +78,19 @@ def test_synthetic_scene_is_deterministic_and_mostly_visible():
     assert abs(cam.tanfovx - 600 / (2 * 1.2 * 600)) < 1e-12
     t = synthetic.make_trajectory(16, 9)
     assert t.ctrl_trans.shape == (10, 3) and torch.equal(t.nu, torch.linspace(0, 1, 16))
+
+
+def test_compat_packages_resolve_to_the_library(monkeypatch):
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "compat"))
+    for name in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C", "gaussian_renderer"):
+        sys.modules.pop(name, None)
+    dgr = importlib.import_module("diff_gaussian_rasterization")
+    knn = importlib.import_module("simple_knn._C")
+    gr = importlib.import_module("gaussian_renderer")
+    assert dgr.GaussianRasterizer is dg.GaussianRasterizer and knn.distCUDA2 is dg.distCUDA2 and gr.render is dg.render
+    for name in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C", "gaussian_renderer"):
+        sys.modules.pop(name, None)
