@@ -297,7 +297,7 @@ int dgs_blur_backward(
     float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
     const int* radii,
     const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
-    const float* dL_dpix, const float* dL_dpixdepth,
+    const float* dL_dpix, const float* dL_dpixdepth, const float* dL_dblur, float blur_denominator,
     char* scratch,
     float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
@@ -340,6 +340,8 @@ int dgs_blur_backward(
     b.point_list = (const uint32_t*)(bin + B.point_list);
     b.dL_dpix = dL_dpix;
     b.dL_dpixdepth = dL_dpixdepth;
+    b.dL_dblur = dL_dblur;
+    b.blur_denominator = blur_denominator;
     char* sc = aligned128(scratch);
     b.g0 = (float4*)sc;
     b.pose_acc = (double*)(sc + align_up(N * 12 * sizeof(float)));
@@ -398,7 +400,7 @@ int dgs_backward(
     return dgs_blur_backward(P, 1, sh_degree, sh_coeffs, num_rendered, background, width, height, means3D, shs,
                              colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp,
                              viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, z_near, z_far, use_sigmoid,
-                             radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpixdepth, scratch,
+                             radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpixdepth, nullptr, 1.0f, scratch,
                              dL_dmeans2D, dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations,
                              dL_dcolors_precomp, dL_dcov3D_precomp, dL_dviewmatrix, dL_dprojmatrix, stream);
 }

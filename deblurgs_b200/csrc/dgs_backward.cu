@@ -94,15 +94,16 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     const uint2 range = p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile];
 
-    __shared__ int s_id[DGS_TILE_PIX];
+    __shared__ uint32_t s_off[DGS_TILE_PIX];   // byte offset of the entry's gradient record (id * 48)
     __shared__ float2 s_xy[DGS_TILE_PIX];
     __shared__ float4 s_con[DGS_TILE_PIX];
     __shared__ float4 s_rgbd[DGS_TILE_PIX];
+    const uint32_t a_off = smem_addr(s_off), a_xy = smem_addr(s_xy), a_con = smem_addr(s_con), a_rgbd = smem_addr(s_rgbd);
 
     const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
     const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
     const float4* __restrict__ geo2 = f.geo2 + (size_t)s * f.P;
-    float* __restrict__ grad_s = grad + (size_t)s * f.P * 12;
+    char* __restrict__ grad_s = reinterpret_cast<char*>(grad + (size_t)s * f.P * 12);
 
     const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
     float T = T_final;
@@ -132,6 +133,11 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             dpix0 = d[pix_id]; dpix1 = d[HW + pix_id]; dpix2 = d[2 * HW + pix_id];
         }
         if (p.dL_dpixdepth) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
+        if (p.dL_dblur) {   // backward of blurred = sum_s color_s / denominator
+            dpix0 += p.dL_dblur[pix_id] / p.blur_denominator;
+            dpix1 += p.dL_dblur[HW + pix_id] / p.blur_denominator;
+            dpix2 += p.dL_dblur[2 * HW + pix_id] / p.blur_denominator;
+        }
     }
     float bg_dot_dpixel = 0.f;
     bg_dot_dpixel += f.background[0] * dpix0;
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             const uint32_t id = p.point_list[range.x + list_len - progress - 1];
             const float4 a = geo0[id];
             const float4 c = geo2[id];
-            s_id[tid] = (int)id;
+            s_off[tid] = id * 48u;
             s_xy[tid] = make_float2(a.x, a.y);
             s_con[tid] = geo1[id];
             s_rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
@@ -178,9 +184,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             float4 con_o;
             float dx, dy, G, alpha;
             if (inside && contributor < last_contributor) {
-                const float2 xy = s_xy[j];
+                const float2 xy = lds_f2(a_xy + 8u * (uint32_t)j);
                 dx = xy.x - pixfx; dy = xy.y - pixfy;
-                con_o = s_con[j];
+                con_o = lds_f4(a_con + 16u * (uint32_t)j);
                 const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
                 if (power <= 0.0f) {
                     G = expf(power);
@@ -190,9 +196,12 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             }
             if (!__any_sync(FULL_MASK, contrib)) continue;
             if (contrib) {
-                T = T / (1.f - alpha);
+                // one IEEE reciprocal shared by T / (1 - alpha) and -T_final / (1 - alpha) (the reference
+                // divides twice; <= 1 ulp apart, far inside the gradient tolerance)
+                const float inv_1ma = 1.0f / (1.f - alpha);
+                T = T * inv_1ma;
                 const float dchannel_dcolor = alpha * T;
-                const float4 cd = s_rgbd[j];
+                const float4 cd = lds_f4(a_rgbd + 16u * (uint32_t)j);
                 float dL_dalpha = 0.0f;
                 acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = cd.x;
                 dL_dalpha += (cd.x - acc0) * dpix0;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
                 dL_dalpha += (cd.w - accd) * dpixd;
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                 const float dL_dG = con_o.w * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
@@ -225,7 +234,8 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
                 for (int k = 0; k < 10; k++) v[k] = 0.f;
             }
             const float total = HalvingReduce<10>::run(v, lane);
-            if (my_comp >= 0) atomicAdd(grad_s + (size_t)s_id[j] * 12 + my_comp, total);
+            if (my_comp >= 0)
+                atomicAdd(reinterpret_cast<float*>(grad_s + lds_u32(a_off + 4u * (uint32_t)j)) + my_comp, total);
           }
         }
     }

@@ -105,6 +105,10 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
             _lib.ptr(color), _lib.ptr(depth), _lib.ptr(radii),
             _lib.ptr(blur), float(blur_denominator),
             C.byref(num_rendered), _stream_ptr(dev))
+    # drop the ctypes callbacks: they close over the _Buffer objects (a reference cycle), and a cycle
+    # would keep hundreds of MB of state buffers alive until Python's cyclic GC runs, forcing the caching
+    # allocator to cudaMalloc fresh blocks every step in the meantime
+    geom.cb = binning.cb = img.cb = None
     _lib.check(rc, "dgs_blur_forward")
     return color, depth, radii, blur, int(num_rendered.value), geom.t, binning.t, img.t
 
@@ -112,7 +116,7 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
 def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacities, scales, rotations,
                       cov3Ds_precomp, viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy,
                       scale_modifier, z_near, z_far, sh_degree, use_sigmoid, radii, geom, binning, img,
-                      grad_color, grad_depth, want_means2D):
+                      grad_color, grad_depth, want_means2D, grad_blur=None, blur_denominator=1.0):
     lib = _lib.load()
     dev = means3D.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -146,7 +150,8 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
             _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos),
             float(tanfovx), float(tanfovy), float(z_near), float(z_far), int(bool(use_sigmoid)),
             _lib.ptr(radii), _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img),
-            _lib.ptr(grad_color), _lib.ptr(grad_depth), _lib.ptr(scratch),
+            _lib.ptr(grad_color), _lib.ptr(grad_depth), _lib.ptr(grad_blur), float(blur_denominator),
+            _lib.ptr(scratch),
             _lib.ptr(dmeans2D), _lib.ptr(dmeans3D), _lib.ptr(dsh), _lib.ptr(dopacity),
             _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
             _lib.ptr(dview), _lib.ptr(dproj), _stream_ptr(dev))
@@ -245,15 +250,13 @@ class _RasterizeBlurry(torch.autograd.Function):
         F = view.shape[0]
         M = sh.shape[1] if sh.numel() != 0 else 0
         gc = _f32c(grad_color) if grad_color is not None else None
-        if grad_blur is not None:
-            # blurred = sum_s color_s / denom  =>  dL/dcolor_s += dL/dblurred / denom
-            gb = (_f32c(grad_blur) / ctx.denom).unsqueeze(0)
-            gc = gb.expand(F, -1, -1, -1).contiguous() if gc is None else gc + gb
+        # blurred = sum_s color_s / denom: its gradient is folded in by the kernel (dL_dblur argument)
+        gb = _f32c(grad_blur) if grad_blur is not None else None
         gd = _f32c(grad_depth) if grad_depth is not None else None
         (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj) = _backward_batched(
             P, F, M, ctx.num_rendered, means3D, sh, colors_c, opac, scales, rot, cov, view, proj, campos, bg,
             rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
-            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D)
+            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D, gb, ctx.denom)
         return (dmeans3D, dmeans2D, dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
                 dview, dproj, None, None, None)
 

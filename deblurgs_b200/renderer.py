@@ -85,12 +85,11 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
     """
     xyz = pc.get_xyz
     F = world_view_transforms.shape[0]
-    screenspace_points = torch.zeros((F,) + tuple(xyz.shape), dtype=xyz.dtype, requires_grad=True,
-                                     device=xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    # Gradient sink for the per-sub-frame screen-space means (the reference allocates zeros_like(xyz)
+    # per sub-frame, gaussian_renderer/__init__.py:26): a zero-stride view, so no F*P*3 zero-fill; its
+    # .grad is the [F,P,3] tensor the backward kernel writes.
+    screenspace_points = torch.zeros(1, dtype=xyz.dtype, device=xyz.device).expand((F,) + tuple(xyz.shape))
+    screenspace_points.requires_grad_(True)
     raster_settings = GaussianRasterizationSettings(
         image_height=int(ref_cam.image_height),
         image_width=int(ref_cam.image_width),

@@ -86,7 +86,9 @@ int dgs_blur_forward(
     int64_t* num_rendered, void* stream);
 
 /*
- * Batched backward.  dL_dpix [F,3,H,W], dL_dpixdepth [F,1,H,W] (either may be NULL = zeros).
+ * Batched backward.  dL_dpix [F,3,H,W], dL_dpixdepth [F,1,H,W] (either may be NULL = zeros);
+ * dL_dblur [3,H,W] or NULL: gradient of the blurred image, folded in as dL_dpix[s] += dL_dblur /
+ * blur_denominator for every sub-frame (the backward of the mean, without materialising [F,3,H,W]).
  * Gaussian gradients are SUMMED over the F sub-frames and written (not accumulated):
  *   dL_dmeans3D [P,3] dL_dsh [P,M,3] dL_dopacity [P,1] dL_dscales [P,3] dL_drotations [P,4]
  *   dL_dcolors_precomp [P,3] dL_dcov3D_precomp [P,6]   (only with the matching precomp input)
@@ -107,7 +109,7 @@ int dgs_blur_backward(
     float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
     const int* radii,
     const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
-    const float* dL_dpix, const float* dL_dpixdepth,
+    const float* dL_dpix, const float* dL_dpixdepth, const float* dL_dblur, float blur_denominator,
     char* scratch,
     float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
