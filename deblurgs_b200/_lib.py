@@ -38,7 +38,7 @@ SIGNATURES = {
     "dgs_backward": (_i, [_i, _i, _i, _i64] + _FWD_COMMON +
                      [_i, _p, _p, _p, _p, _p, _p, _p] + [_p] * 10 + [_p]),
     "dgs_debug_geometry": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "dgs_debug_binning": (_i, [_p, _i64, _p, _p, _p]),
+    "dgs_debug_binning": (_i, [_p, _p, _i, _i, _i, _i, _i64, _p, _p, _p]),
     "dgs_debug_image": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "dgs_profile_enable": (_i, [_i]),
     "dgs_profile_num_stages": (_i, []),

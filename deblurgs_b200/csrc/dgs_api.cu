@@ -6,6 +6,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -90,8 +92,18 @@ GeomLayout geom_layout(size_t N)
     L.offsets = o; o = align_up(o + N * sizeof(uint32_t));
     size_t tmp = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)N);
+    tmp += 1024;   // the permuted-input scan may ask for a little more than the plain one
     L.scan_temp_bytes = tmp;
     L.scan_temp = o; o = align_up(o + tmp);
+    L.dkeys = o; o = align_up(o + N * sizeof(uint64_t));
+    L.dkeys_sorted = o; o = align_up(o + N * sizeof(uint64_t));
+    L.order_in = o; o = align_up(o + N * sizeof(uint32_t));
+    L.order = o; o = align_up(o + N * sizeof(uint32_t));
+    size_t tmp2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)N);
+    L.sort_temp_bytes = tmp2;
+    L.sort_temp = o; o = align_up(o + tmp2);
     L.total = o + 128;
     return L;
 }
@@ -100,11 +112,11 @@ BinLayout bin_layout(size_t D)
     BinLayout L;
     size_t o = 0;
     L.point_list = o; o = align_up(o + D * sizeof(uint32_t));
-    L.keys = o; o = align_up(o + D * sizeof(uint64_t));
-    L.keys_unsorted = o; o = align_up(o + D * sizeof(uint64_t));
+    L.keys = o; o = align_up(o + D * sizeof(uint32_t));
+    L.keys_unsorted = o; o = align_up(o + D * sizeof(uint32_t));
     L.vals_unsorted = o; o = align_up(o + D * sizeof(uint32_t));
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint64_t*)nullptr, (uint64_t*)nullptr,
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)D);
     L.sort_temp_bytes = tmp;
     L.sort_temp = o; o = align_up(o + tmp);
@@ -167,7 +179,17 @@ static void bind_geom(FwdParams& p, char* geom, const GeomLayout& G)
     p.geo2 = (float4*)(geom + G.geo2);
     p.tiles = (uint32_t*)(geom + G.tiles);
     p.offsets = (uint32_t*)(geom + G.offsets);
+    p.dkeys = (uint64_t*)(geom + G.dkeys);
+    p.order_in = (uint32_t*)(geom + G.order_in);
+    p.order = (uint32_t*)(geom + G.order);
 }
+
+// tiles[order[i]]: input of the scan over the depth-sorted entry order
+struct PermutedTiles {
+    const uint32_t* tiles;
+    const uint32_t* order;
+    __host__ __device__ uint32_t operator()(uint32_t i) const { return tiles[order[i]]; }
+};
 
 }  // namespace dgs
 
@@ -237,10 +259,21 @@ int dgs_blur_forward(
     int64_t D = 0;
     if (N > 0) {
         { StageTimer t(ST_PREPROCESS_FWD, st, 1); launch_preprocess_fwd(p, sh_degree, st); }
+        {
+            // stage 1 of the binning: depth order of the (sub-frame, Gaussian) entries
+            StageTimer t(ST_SORT, st, 0);
+            size_t tmp1 = G.sort_temp_bytes;
+            DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, p.dkeys,
+                                                     (uint64_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
+                                                     (int64_t)N, 0, 32 + sf_bits, st),
+                     "depth sort");
+        }
         size_t tmp = G.scan_temp_bytes;
         {
             StageTimer t(ST_SCAN, st, 0);
-            DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, p.tiles, p.offsets, (int64_t)N, st), "scan");
+            auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0u),
+                                                      PermutedTiles{p.tiles, p.order});
+            DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, in, p.offsets, (int64_t)N, st), "scan");
         }
         uint32_t total = 0;
         // The one host synchronisation of the batched forward (the reference does one per
@@ -256,8 +289,8 @@ int dgs_blur_forward(
     if (!bin) return fail(DGS_ERR_ALLOC, "binning buffer allocation failed");
     bin = aligned128(bin);
     uint32_t* point_list = (uint32_t*)(bin + B.point_list);
-    uint64_t* keys = (uint64_t*)(bin + B.keys);
-    uint64_t* keys_unsorted = (uint64_t*)(bin + B.keys_unsorted);
+    uint32_t* keys = (uint32_t*)(bin + B.keys);
+    uint32_t* keys_unsorted = (uint32_t*)(bin + B.keys_unsorted);
     uint32_t* vals_unsorted = (uint32_t*)(bin + B.vals_unsorted);
 
     if (F > 0 && tiles > 0)
@@ -266,10 +299,11 @@ int dgs_blur_forward(
         { StageTimer t(ST_DUPLICATE, st, 1); launch_duplicate(p, keys_unsorted, vals_unsorted, st); }
         size_t tmp = B.sort_temp_bytes;
         {
+            // stage 2: stable sort of the duplicates on the short [sub-frame | tile] key
             StageTimer t(ST_SORT, st, 0);
             DGS_CUDA(cub::DeviceRadixSort::SortPairs(bin + B.sort_temp, tmp, keys_unsorted, keys, vals_unsorted,
-                                                     point_list, (int64_t)D, 0, 32 + p.tile_bits + sf_bits, st),
-                     "radix sort");
+                                                     point_list, (int64_t)D, 0, p.tile_bits + sf_bits, st),
+                     "tile sort");
         }
         { StageTimer t(ST_TILE_RANGES, st, 1); launch_tile_ranges(D, keys, p.tile_bits, (int)tiles, ranges, st); }
     }
@@ -521,15 +555,26 @@ int dgs_debug_geometry(const char* geom_buffer, int P, int F, float* depths, flo
     return DGS_OK;
 }
 
-int dgs_debug_binning(const char* binning_buffer, int64_t num_rendered, uint64_t* keys,
-                      uint32_t* point_list, void* stream)
+int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, int P, int F, int width, int height,
+                      int64_t num_rendered, uint64_t* keys, uint32_t* point_list, void* stream)
 {
     if (num_rendered <= 0) return DGS_OK;
-    if (!binning_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null binning buffer");
+    if (!binning_buffer || !geom_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null state buffer");
     const BinLayout B = bin_layout((size_t)num_rendered);
     char* bin = aligned128((char*)binning_buffer);
     cudaStream_t st = (cudaStream_t)stream;
-    if (keys) DGS_CUDA(cudaMemcpyAsync(keys, bin + B.keys, num_rendered * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st), "copy keys");
+    if (keys) {
+        FwdParams p;
+        memset(&p, 0, sizeof(p));
+        p.P = P; p.F = F; p.W = width; p.H = height;
+        p.tiles_x = (width + DGS_TILE_X - 1) / DGS_TILE_X;
+        p.tiles_y = (height + DGS_TILE_Y - 1) / DGS_TILE_Y;
+        p.tile_bits = ref_tile_bits((uint32_t)(p.tiles_x * p.tiles_y));
+        bind_geom(p, aligned128((char*)geom_buffer), geom_layout((size_t)P * F));
+        launch_rebuild_keys(p, num_rendered, (const uint32_t*)(bin + B.keys), (const uint32_t*)(bin + B.point_list),
+                            keys, st);
+        DGS_CUDA(cudaGetLastError(), "rebuild keys");
+    }
     if (point_list) DGS_CUDA(cudaMemcpyAsync(point_list, bin + B.point_list, num_rendered * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy list");
     return DGS_OK;
 }

@@ -159,9 +159,11 @@ int dgs_debug_geometry(const char* geom_buffer, int P, int F,
                        float* depths, float* means2D, float* conic_opacity, float* rgb,
                        float* clamped, uint32_t* tiles_touched, uint32_t* point_offsets,
                        void* stream);
-/*   keys [D] u64 (batched key: sub-frame | tile | depth bits), point_list [D] u32 */
-int dgs_debug_binning(const char* binning_buffer, int64_t num_rendered,
-                      uint64_t* keys, uint32_t* point_list, void* stream);
+/*   keys [D] u64 (batched key of every sorted list entry: sub-frame | tile | depth bits; the library
+ *   sorts in two stages -- depth first, then a stable sort on sub-frame | tile -- so the 64-bit key
+ *   is rebuilt here from the sorted 32-bit key and the entry's depth), point_list [D] u32 */
+int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, int P, int F, int width, int height,
+                      int64_t num_rendered, uint64_t* keys, uint32_t* point_list, void* stream);
 /*   ranges [F,tiles,2] u32 (absolute positions in the batched list), final_T [F,H,W],
  *   n_contrib [F,H,W] u32 */
 int dgs_debug_image(const char* image_buffer, int F, int width, int height,

@@ -66,7 +66,7 @@ def ours_decode(fw, P, F, W, H):
                                           p(d["conic_opacity"]), p(d["rgb"]), p(d["clamped"]),
                                           p(d["tiles_touched"]), p(d["point_offsets"]), st), "debug_geometry")
     if D:
-        _lib.check(lib.dgs_debug_binning(p(fw["binning"]), D, p(d["keys"]), p(d["point_list"]), st), "debug_binning")
+        _lib.check(lib.dgs_debug_binning(p(fw["geom"]), p(fw["binning"]), P, F, W, H, D, p(d["keys"]), p(d["point_list"]), st), "debug_binning")
     _lib.check(lib.dgs_debug_image(p(fw["img"]), F, W, H, p(d["ranges"]), p(d["final_T"]), p(d["n_contrib"]), st),
                "debug_image")
     tb, sb = C.c_int(0), C.c_int(0)
