@@ -76,9 +76,83 @@ struct HalvingReduce {
 // warp owns an 8x4 pixel rectangle and, like the forward, evaluates only the staged entries
 // whose alpha >= 1/255 footprint can reach that rectangle.  grad = AoS float[N][12]:
 //   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7,8,9 dcolor | 10,11 unused
+//
+// Gradient accumulation is split in two phases so that no per-entry cross-lane reduction is
+// needed (the reference issues 10 atomics per contributing pixel; a per-entry warp reduction
+// costs ~50 shuffle/select/add instructions per (warp, entry)):
+//   phase 1 (lane = pixel): replay the list back to front exactly like the reference and, for
+//           every entry with a contributing pixel, append ONE column to a per-warp queue in
+//           shared memory: per pixel the two scalars w1 = opacity*G*dL/dalpha and w2 = alpha*T
+//           (zeros where the pixel does not contribute), plus the entry's (xy, conic, opacity,
+//           record offset).
+//   phase 2 (lane = queued entry, when 16 entries are queued): each lane walks the pixels of
+//           the rectangle (two half-warps take 16 pixels each), accumulates the six moments
+//           sum w1*{1,dx,dy,dx^2,dx*dy,dy^2} and sum w2*dL/dpix{r,g,b,depth} in registers with
+//           every lane busy, converts them to the 10 gradient components and issues the REDs.
+// All sums are over the same terms as the reference's; only their order differs.
 // ---------------------------------------------------------------------------------------
+#define BWD_QN 16                 // queued entries per flush
+#define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
+
+struct BwdSmem {
+    uint32_t off[DGS_TILE_PIX];
+    float2 xy[DGS_TILE_PIX];
+    float4 con[DGS_TILE_PIX];
+    float4 rgbd[DGS_TILE_PIX];
+    float2 qw[8][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
+    float4 qg0[8][BWD_QN];               // x, y, conic.x, conic.y
+    float4 qg1[8][BWD_QN];               // conic.z, opacity, record offset (bits), -
+    float4 dpix[8][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
+    int tile_max;
+};
+
+__device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned lane, int qn, float wx0f,
+                                          float wy0f, float ddelx_dx, float ddely_dy, char* __restrict__ grad_s)
+{
+    __syncwarp();
+    const unsigned e = lane & 15u, half = lane >> 4;
+    const float4 g0 = sm.qg0[warp][e];
+    const float4 g1 = sm.qg1[warp][e];
+    // pixel p = half*16 + pp of the 8x4 rectangle: x = wx0 + (p & 7), y = wy0 + (p >> 3)
+    const float bx = g0.x - wx0f, by = g0.y - (wy0f + 2.0f * (float)half);
+    float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 16; pp++) {
+        const float2 w = sm.qw[warp][e][half * 16 + pp];
+        const float4 dp = sm.dpix[warp][half * 16 + pp];
+        const float dx = bx - (float)(pp & 7), dy = by - (float)(pp >> 3);
+        const float tx = w.x * dx, ty = w.x * dy;
+        S0 += w.x; Sx += tx; Sy += ty;
+        Sxx += tx * dx; Sxy += tx * dy; Syy += ty * dy;
+        Cr += w.y * dp.x; Cg += w.y * dp.y; Cb += w.y * dp.z; Cd += w.y * dp.w;
+    }
+    S0 += __shfl_xor_sync(FULL_MASK, S0, 16);   Sx += __shfl_xor_sync(FULL_MASK, Sx, 16);
+    Sy += __shfl_xor_sync(FULL_MASK, Sy, 16);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, 16);
+    Sxy += __shfl_xor_sync(FULL_MASK, Sxy, 16); Syy += __shfl_xor_sync(FULL_MASK, Syy, 16);
+    Cr += __shfl_xor_sync(FULL_MASK, Cr, 16);   Cg += __shfl_xor_sync(FULL_MASK, Cg, 16);
+    Cb += __shfl_xor_sync(FULL_MASK, Cb, 16);   Cd += __shfl_xor_sync(FULL_MASK, Cd, 16);
+    if (half == 0 && (int)e < qn) {
+        const float A = g0.z, B = g0.w, Cc = g1.x, o = g1.y;
+        float* rec = reinterpret_cast<float*>(grad_s + __float_as_uint(g1.z));
+        atomicAdd(rec + 0, -(A * Sx + B * Sy) * ddelx_dx);
+        atomicAdd(rec + 1, -(Cc * Sy + B * Sx) * ddely_dy);
+        atomicAdd(rec + 2, -0.5f * Sxx);
+        atomicAdd(rec + 3, -0.5f * Sxy);
+        atomicAdd(rec + 4, -0.5f * Syy);
+        atomicAdd(rec + 5, o != 0.f ? S0 / o : 0.f);
+        atomicAdd(rec + 6, Cd);
+        atomicAdd(rec + 7, Cr);
+        atomicAdd(rec + 8, Cg);
+        atomicAdd(rec + 9, Cb);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __restrict__ grad)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+
     const FwdParams& f = p.f;
     const int s = blockIdx.z;
     const int tile = blockIdx.y * f.tiles_x + blockIdx.x;
@@ -93,12 +167,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
     const float pixfx = (float)pixx, pixfy = (float)pixy;
 
     const uint2 range = p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile];
-
-    __shared__ uint32_t s_off[DGS_TILE_PIX];   // byte offset of the entry's gradient record (id * 48)
-    __shared__ float2 s_xy[DGS_TILE_PIX];
-    __shared__ float4 s_con[DGS_TILE_PIX];
-    __shared__ float4 s_rgbd[DGS_TILE_PIX];
-    const uint32_t a_off = smem_addr(s_off), a_xy = smem_addr(s_xy), a_con = smem_addr(s_con), a_rgbd = smem_addr(s_rgbd);
+    const uint32_t a_xy = smem_addr(sm.xy), a_con = smem_addr(sm.con), a_rgbd = smem_addr(sm.rgbd);
 
     const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
     const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
@@ -111,20 +180,14 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     // Nothing behind the deepest contributor of the tile can receive gradient: restrict the
     // replay to the first `tile_max` list entries (identical results, less staging).
-    __shared__ int s_max;
-    if (tid == 0) s_max = 0;
+    if (tid == 0) sm.tile_max = 0;
     __syncthreads();
-    {
-        int m = last_contributor;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
-        if (lane == 0) atomicMax(&s_max, m);
-    }
-    __syncthreads();
-    const int list_len = min((int)(range.y - range.x), s_max);
     int warp_max = last_contributor;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) warp_max = max(warp_max, __shfl_xor_sync(FULL_MASK, warp_max, d));
+    if (lane == 0) atomicMax(&sm.tile_max, warp_max);
+    __syncthreads();
+    const int list_len = min((int)(range.y - range.x), sm.tile_max);
 
     float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpixd = 0.f;
     if (inside) {
@@ -139,6 +202,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             dpix2 += p.dL_dblur[2 * HW + pix_id] / p.blur_denominator;
         }
     }
+    sm.dpix[warp][lane] = make_float4(dpix0, dpix1, dpix2, dpixd);
     float bg_dot_dpixel = 0.f;
     bg_dot_dpixel += f.background[0] * dpix0;
     bg_dot_dpixel += f.background[1] * dpix1;
@@ -151,7 +215,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     const int rounds = (list_len + DGS_TILE_PIX - 1) / DGS_TILE_PIX;
     int todo = list_len;
-    const int my_comp = HalvingReduce<10>::owner(lane);
+    int qn = 0;   // queued entries of this warp (warp-uniform)
 
     for (int i = 0; i < rounds; i++, todo -= DGS_TILE_PIX) {
         __syncthreads();
@@ -160,93 +224,87 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             const uint32_t id = p.point_list[range.x + list_len - progress - 1];
             const float4 a = geo0[id];
             const float4 c = geo2[id];
-            s_off[tid] = id * 48u;
-            s_xy[tid] = make_float2(a.x, a.y);
-            s_con[tid] = geo1[id];
-            s_rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
+            sm.off[tid] = id * 48u;
+            sm.xy[tid] = make_float2(a.x, a.y);
+            sm.con[tid] = geo1[id];
+            sm.rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
         }
         __syncthreads();
         const int batch = min(DGS_TILE_PIX, todo);
         // entry j of this batch sits at list position first_pos - j (the batch is staged back to front)
         const int first_pos = list_len - i * DGS_TILE_PIX - 1;
         for (int c0 = 0; c0 < batch; c0 += 32) {
-          const int jl = c0 + (int)lane;
-          bool keep = false;
-          if (jl < batch && first_pos - jl < warp_max)
-              keep = entry_reaches_rect(s_xy[jl], s_con[jl], rx0, ry0, rx1, ry1);
-          unsigned mask = __ballot_sync(FULL_MASK, keep);
-          while (mask) {
-            const int j = c0 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int contributor = first_pos - j;
-            float v[10];
-            bool contrib = false;
-            float4 con_o;
-            float dx, dy, G, alpha;
-            if (inside && contributor < last_contributor) {
+            const int jl = c0 + (int)lane;
+            bool keep = false;
+            if (jl < batch && first_pos - jl < warp_max)
+                keep = entry_reaches_rect(sm.xy[jl], sm.con[jl], rx0, ry0, rx1, ry1);
+            unsigned mask = __ballot_sync(FULL_MASK, keep);
+            while (mask) {
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int contributor = first_pos - j;
                 const float2 xy = lds_f2(a_xy + 8u * (uint32_t)j);
-                dx = xy.x - pixfx; dy = xy.y - pixfy;
-                con_o = lds_f4(a_con + 16u * (uint32_t)j);
-                const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
-                if (power <= 0.0f) {
-                    G = expf(power);
-                    alpha = min(0.99f, con_o.w * G);
-                    contrib = alpha >= 1.0f / 255.0f;
+                const float4 con_o = lds_f4(a_con + 16u * (uint32_t)j);
+                const float dx = xy.x - pixfx, dy = xy.y - pixfy;
+                bool contrib = false;
+                float G = 0.f, alpha = 0.f;
+                if (inside && contributor < last_contributor) {
+                    const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+                    if (power <= 0.0f) {
+                        G = expf(power);
+                        alpha = min(0.99f, con_o.w * G);
+                        contrib = alpha >= 1.0f / 255.0f;
+                    }
+                }
+                if (!__any_sync(FULL_MASK, contrib)) continue;
+                float w1 = 0.f, w2 = 0.f;
+                if (contrib) {
+                    // one IEEE reciprocal shared by T / (1 - alpha) and -T_final / (1 - alpha) (the
+                    // reference divides twice; <= 1 ulp apart, far inside the gradient tolerance)
+                    const float inv_1ma = 1.0f / (1.f - alpha);
+                    T = T * inv_1ma;
+                    w2 = alpha * T;
+                    const float4 cd = lds_f4(a_rgbd + 16u * (uint32_t)j);
+                    float dL_dalpha = 0.0f;
+                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = cd.x;
+                    dL_dalpha += (cd.x - acc0) * dpix0;
+                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = cd.y;
+                    dL_dalpha += (cd.y - acc1) * dpix1;
+                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cd.z;
+                    dL_dalpha += (cd.z - acc2) * dpix2;
+                    accd = last_alpha * last_depth + (1.f - last_alpha) * accd; last_depth = cd.w;
+                    dL_dalpha += (cd.w - accd) * dpixd;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
+                    w1 = con_o.w * dL_dalpha * G;
+                }
+                sm.qw[warp][qn][lane] = make_float2(w1, w2);
+                if (lane == 0) {
+                    sm.qg0[warp][qn] = make_float4(xy.x, xy.y, con_o.x, con_o.y);
+                    sm.qg1[warp][qn] = make_float4(con_o.z, con_o.w, __uint_as_float(sm.off[j]), 0.f);
+                }
+                if (++qn == BWD_QN) {
+                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, grad_s);
+                    qn = 0;
                 }
             }
-            if (!__any_sync(FULL_MASK, contrib)) continue;
-            if (contrib) {
-                // one IEEE reciprocal shared by T / (1 - alpha) and -T_final / (1 - alpha) (the reference
-                // divides twice; <= 1 ulp apart, far inside the gradient tolerance)
-                const float inv_1ma = 1.0f / (1.f - alpha);
-                T = T * inv_1ma;
-                const float dchannel_dcolor = alpha * T;
-                const float4 cd = lds_f4(a_rgbd + 16u * (uint32_t)j);
-                float dL_dalpha = 0.0f;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = cd.x;
-                dL_dalpha += (cd.x - acc0) * dpix0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = cd.y;
-                dL_dalpha += (cd.y - acc1) * dpix1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cd.z;
-                dL_dalpha += (cd.z - acc2) * dpix2;
-                accd = last_alpha * last_depth + (1.f - last_alpha) * accd; last_depth = cd.w;
-                dL_dalpha += (cd.w - accd) * dpixd;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-
-                const float dL_dG = con_o.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
-                v[6] = dchannel_dcolor * dpixd;
-                v[7] = dchannel_dcolor * dpix0;
-                v[8] = dchannel_dcolor * dpix1;
-                v[9] = dchannel_dcolor * dpix2;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 10; k++) v[k] = 0.f;
-            }
-            const float total = HalvingReduce<10>::run(v, lane);
-            if (my_comp >= 0)
-                atomicAdd(reinterpret_cast<float*>(grad_s + lds_u32(a_off + 4u * (uint32_t)j)) + my_comp, total);
-          }
         }
     }
+    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, grad_s);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_render_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+        configured = true;
+    }
     dim3 grid(f.tiles_x, f.tiles_y, f.F), block(DGS_TILE_PIX);
-    k_render_bwd<<<grid, block, 0, st>>>(p, reinterpret_cast<float*>(p.g0));
+    k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p, reinterpret_cast<float*>(p.g0));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -300,13 +358,35 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     const int my_comp = HalvingReduce<NPOSE>::owner(lane);
     const int my_slot = my_comp >= 0 ? kPoseSlot[my_comp] : -1;
 
+    // Software pipeline: the per-(sub-frame, Gaussian) record of iteration s+1 (radius, 48-B gradient,
+    // clamp mask) is requested while iteration s computes.  The kernel runs at one 256-thread block
+    // per SM (register-limited), so without this every iteration exposes a full DRAM round trip.
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int nx_radius = 0;
+    float4 nx_a = zero4, nx_b = zero4, nx_c = zero4;
+    unsigned nx_mask = 0;
+    auto fetch = [&](int s) {
+        const size_t n = (size_t)s * f.P + gi;
+        nx_radius = live ? f.radii[n] : 0;
+        if (nx_radius > 0) {
+            nx_a = reinterpret_cast<const float4*>(grad)[n * 3];
+            nx_b = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
+            nx_c = reinterpret_cast<const float4*>(grad)[n * 3 + 2];
+            nx_mask = __float_as_uint(reinterpret_cast<const float*>(f.geo2 + n)[3]);
+        }
+    };
+    if (f.F > 0) fetch(0);
+
     for (int s = 0; s < f.F; s++) {
         const size_t n = (size_t)s * f.P + gi;
-        const bool vis = live && f.radii[n] > 0;
+        const bool vis = nx_radius > 0;
+        const float4 ga = nx_a, gb = nx_b, gc = nx_c;
+        const unsigned cur_mask = nx_mask;
+        if (s + 1 < f.F) fetch(s + 1);
         if (p.dL_dmeans2D != nullptr && live) {
-            float gx = 0.f, gy = 0.f;
-            if (vis) { gx = grad[n * 12]; gy = grad[n * 12 + 1]; }
-            p.dL_dmeans2D[n * 3] = gx; p.dL_dmeans2D[n * 3 + 1] = gy; p.dL_dmeans2D[n * 3 + 2] = 0.f;
+            p.dL_dmeans2D[n * 3] = vis ? ga.x : 0.f;
+            p.dL_dmeans2D[n * 3 + 1] = vis ? ga.y : 0.f;
+            p.dL_dmeans2D[n * 3 + 2] = 0.f;
         }
         if (!__any_sync(FULL_MASK, vis)) continue;
         float pv[NPOSE];
@@ -315,9 +395,6 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
         if (vis) {
             const float* __restrict__ V = f.view + 16 * s;
             const float* __restrict__ PM = f.proj + 16 * s;
-            const float4 ga = reinterpret_cast<const float4*>(grad)[n * 3];
-            const float4 gb = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
-            const float4 gc = reinterpret_cast<const float4*>(grad)[n * 3 + 2];
             const float dm2x = ga.x, dm2y = ga.y;
             const float3 dconic = {ga.z, ga.w, gb.x};
             dopac += gb.y;
@@ -407,7 +484,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
                 const float3 dir_orig = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
                 const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
                 const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-                const unsigned mask = __float_as_uint(f.geo2[n].w);
+                const unsigned mask = cur_mask;
                 float dRGB[3] = {dcol.x, dcol.y, dcol.z};
                 if (f.use_sigmoid) {
                     // recompute the pre-activation colour
