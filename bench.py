@@ -364,6 +364,10 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = eff_world * args.steps / float(t_e2e.item())
 
+    if eff_world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     clocks = sampler.summary()

@@ -1,0 +1,69 @@
+"""Multi-GPU check of the sub-frame-sharded blurry view (run under torchrun on a GPU box):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_gpu_check.py [config]
+
+Every rank renders its contiguous block of sub-frames (deblurgs_b200.dist.render_blurry_sharded), the partial
+blurry images are all-reduced over NCCL, every rank evaluates the same L1 loss, and the Gaussian / control-point
+gradients are all-reduced.  Rank 0 compares the result with the unsharded computation on its own GPU.
+"""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from deblurgs_b200 import dist as dd  # noqa: E402
+
+
+def main():
+    cfg = sys.argv[1] if len(sys.argv) > 1 else "small"
+    rank, world, local = bench.dist_setup(0)
+    dev = torch.device("cuda", local)
+    w = bench.build_workload(cfg, 0, dev)          # same view on every rank (seed independent of rank)
+    cmm, g = w["cmm"], w["gaussians"]
+    gt = w["gt_host"].to(dev)
+    params = g.parameters() + cmm.parameters()
+
+    def run(sharded):
+        for p in params:
+            p.grad = None
+        if sharded:
+            blurred, pkg, (a, b) = dd.render_blurry_sharded(cmm, 0, w["bg"])
+        else:
+            blurred = cmm.query(0, "all", background=w["bg"])["blurred"]
+        loss = (blurred - gt).abs().mean()
+        loss.backward()
+        grads = [p.grad.clone() for p in params]
+        if sharded and world > 1:
+            for t in grads:
+                dist.all_reduce(t)
+        return blurred.detach(), loss.detach(), grads
+
+    b1, l1, g1 = run(True)
+    # timing of the sharded step (max over ranks)
+    torch.cuda.synchronize(); dist.barrier() if world > 1 else None
+    t0 = time.perf_counter()
+    for _ in range(10):
+        run(True)
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / 10], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        b0, l0, g0 = run(False)
+        err_img = (b0 - b1).abs().max().item()
+        rel = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item() for a, b in zip(g1, g0))
+        print("config %s world %d: sharded step %.2f ms; blurred max-abs diff %.2e; loss %.6f vs %.6f; "
+              "max gradient rel diff %.2e" % (cfg, world, dt.item() * 1e3, err_img, l1.item(), l0.item(), rel))
+        assert err_img <= 1e-5 and rel <= 1e-3
+        print("OK")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
