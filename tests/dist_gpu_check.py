@@ -3,7 +3,7 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_gpu_check.py [config]
 
 Every rank renders its contiguous block of sub-frames (deblurgs_b200.dist.render_blurry_sharded), the partial
-blurry images are all-reduced over NCCL, every rank evaluates the same L1 loss, and the Gaussian / control-point
+blurry images are all-reduced over NCCL, every rank evaluates the same (L2) loss, and the Gaussian / control-point
 gradients are all-reduced.  Rank 0 compares the result with the unsharded computation on its own GPU.
 """
 import os
@@ -34,7 +34,10 @@ def main():
             blurred, pkg, (a, b) = dd.render_blurry_sharded(cmm, 0, w["bg"])
         else:
             blurred = cmm.query(0, "all", background=w["bg"])["blurred"]
-        loss = (blurred - gt).abs().mean()
+        # smooth (L2) loss for the equality check: with L1, sign(blurred - gt) flips on the handful of
+        # pixels where the two summation orders of the blurred image straddle gt (seen at 1080p: a few
+        # Gaussians move by ~1e-3 of the max gradient although both paths are exact)
+        loss = ((blurred - gt) ** 2).mean()
         loss.backward()
         grads = [p.grad.clone() for p in params]
         if sharded and world > 1:
