@@ -335,7 +335,7 @@ int dgs_blur_backward(
     char* scratch,
     float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
-    float* dL_dviewmatrix, float* dL_dprojmatrix, void* stream)
+    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     BwdParams b;
@@ -383,6 +383,7 @@ int dgs_blur_backward(
     b.dL_dscales = dL_dscales; b.dL_drotations = dL_drotations;
     b.dL_dcolors_precomp = dL_dcolors_precomp; b.dL_dcov3D_precomp = dL_dcov3D_precomp;
     b.dL_dview = dL_dviewmatrix; b.dL_dproj = dL_dprojmatrix;
+    b.densify_stats = densify_stats;
 
     {
         StageTimer t(ST_BWD_MEMSET, st, 0);
@@ -436,7 +437,7 @@ int dgs_backward(
                              viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, z_near, z_far, use_sigmoid,
                              radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpixdepth, nullptr, 1.0f, scratch,
                              dL_dmeans2D, dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations,
-                             dL_dcolors_precomp, dL_dcov3D_precomp, dL_dviewmatrix, dL_dprojmatrix, stream);
+                             dL_dcolors_precomp, dL_dcov3D_precomp, dL_dviewmatrix, dL_dprojmatrix, nullptr, stream);
 }
 
 // ---- profiling / measurement ------------------------------------------------------------

@@ -355,6 +355,8 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dopac = 0.f;
     float3 dcolor_acc = {0.f, 0.f, 0.f};
+    float st_norm = 0.f, st_count = 0.f;   // densification statistics (train.py:188-193 of the reference)
+    int st_radius = 0;
     const int my_comp = HalvingReduce<NPOSE>::owner(lane);
     const int my_slot = my_comp >= 0 ? kPoseSlot[my_comp] : -1;
 
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     for (int s = 0; s < f.F; s++) {
         const size_t n = (size_t)s * f.P + gi;
         const bool vis = nx_radius > 0;
+        const int nx_radius_cur = nx_radius;
         const float4 ga = nx_a, gb = nx_b, gc = nx_c;
         const unsigned cur_mask = nx_mask;
         if (s + 1 < f.F) fetch(s + 1);
@@ -398,6 +401,9 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
             const float dm2x = ga.x, dm2y = ga.y;
             const float3 dconic = {ga.z, ga.w, gb.x};
             dopac += gb.y;
+            st_norm += sqrtf(ga.x * ga.x + ga.y * ga.y);
+            st_count += 1.0f;
+            st_radius = max(st_radius, nx_radius_cur);
             const float ddepth = gb.z;
             float3 dcol = {gb.w, gc.x, gc.y};
 
@@ -596,6 +602,9 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
 
     p.dL_dmeans3D[3 * g] = dmean.x; p.dL_dmeans3D[3 * g + 1] = dmean.y; p.dL_dmeans3D[3 * g + 2] = dmean.z;
     p.dL_dopacity[g] = dopac;
+    if (p.densify_stats != nullptr) {
+        p.densify_stats[3 * g] = st_norm; p.densify_stats[3 * g + 1] = st_count; p.densify_stats[3 * g + 2] = (float)st_radius;
+    }
     if (DEG >= 0) {
         float* dst = p.dL_dsh + (size_t)g * f.M * 3;
 #pragma unroll

@@ -87,6 +87,39 @@ class GaussianParams:
     def parameters(self):
         return [self._xyz, self._features_dc, self._features_rest, self._scaling, self._rotation, self._opacity]
 
+    # ---- densification bookkeeping (reference: scene/gaussian_model.py:456-458, train.py:188-193)
+    def _ensure_stats(self):
+        if not hasattr(self, "xyz_gradient_accum"):
+            P, dev = self._xyz.shape[0], self._xyz.device
+            self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+            self.denom = torch.zeros((P, 1), device=dev)
+            self.max_radii2D = torch.zeros(P, device=dev)
+
+    def add_densification_stats(self, viewspace_point_tensor, update_filter, denom_count):
+        """Reference semantics, one sub-frame at a time. `viewspace_point_tensor` may be the [F,P,3] sink of
+        a batched render together with its sub-frame index: pass `(tensor, s)`."""
+        self._ensure_stats()
+        if isinstance(viewspace_point_tensor, tuple):
+            t, s = viewspace_point_tensor
+            grad = t.grad[s]
+        else:
+            grad = viewspace_point_tensor.grad
+        self.xyz_gradient_accum[update_filter] += torch.norm(grad[update_filter, :2], dim=-1, keepdim=True)
+        self.denom[update_filter] += denom_count
+
+    @torch.no_grad()
+    def add_densification_stats_blurry(self, pkg):
+        """The whole loop `for render_pkg in render_pkgs: max_radii2D[...] = max(...);
+        add_densification_stats(..., 1/len(render_pkgs))` of the reference (train.py:188-193) for one batched
+        render, from the statistics the backward kernel produced in the same pass."""
+        self._ensure_stats()
+        st = pkg["densification"]
+        if not st.ready:
+            raise RuntimeError("densification statistics are produced by the backward pass: call loss.backward() first")
+        self.xyz_gradient_accum += st.grad_norm_sum
+        self.denom += st.visible_count / float(st.num_subframes)
+        self.max_radii2D = torch.max(self.max_radii2D, st.max_radius.to(self.max_radii2D.dtype))
+
     @property
     def get_xyz(self):
         return self._xyz

@@ -116,7 +116,7 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
 def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacities, scales, rotations,
                       cov3Ds_precomp, viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy,
                       scale_modifier, z_near, z_far, sh_degree, use_sigmoid, radii, geom, binning, img,
-                      grad_color, grad_depth, want_means2D, grad_blur=None, blur_denominator=1.0):
+                      grad_color, grad_depth, want_means2D, grad_blur=None, blur_denominator=1.0, want_stats=False):
     lib = _lib.load()
     dev = means3D.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -137,8 +137,9 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
     dcov = alloc((P, 6), **f32) if has_cov else None
     dview = alloc((F, 4, 4), **f32)
     dproj = alloc((F, 4, 4), **f32)
+    stats = alloc((P, 3), **f32) if want_stats else None
     if P == 0 or F == 0:
-        return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj
+        return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, stats
     scratch = torch.empty(int(lib.dgs_blur_backward_scratch_bytes(P, F)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.dgs_blur_backward(
@@ -154,9 +155,9 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
             _lib.ptr(scratch),
             _lib.ptr(dmeans2D), _lib.ptr(dmeans3D), _lib.ptr(dsh), _lib.ptr(dopacity),
             _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
-            _lib.ptr(dview), _lib.ptr(dproj), _stream_ptr(dev))
+            _lib.ptr(dview), _lib.ptr(dproj), _lib.ptr(stats), _stream_ptr(dev))
     _lib.check(rc, "dgs_blur_backward")
-    return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj
+    return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, stats
 
 
 def _empty_like_input(t):
@@ -197,7 +198,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         M = sh.shape[1] if sh.numel() != 0 else 0
         gc = _f32c(grad_out_color) if grad_out_color is not None else None
         gd = _f32c(grad_out_depth) if grad_out_depth is not None else None
-        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj) = _backward_batched(
+        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, _) = _backward_batched(
             P, 1, M, ctx.num_rendered, means3D, sh, colors_c, opac, scales, rot, cov, view, proj, campos, bg,
             rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
             rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, True)
@@ -221,8 +222,9 @@ class _RasterizeBlurry(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                viewmatrix, projmatrix, campos, raster_settings, blur_denominator):
+                viewmatrix, projmatrix, campos, raster_settings, blur_denominator, stats_holder=None):
         rs = raster_settings
+        ctx.stats_holder = stats_holder
         means3D_c, sh_c, colors_c = _f32c(means3D), _f32c(sh), _f32c(colors_precomp)
         opac_c, scales_c, rot_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
         view_c, proj_c, campos_c, bg_c = _f32c(viewmatrix), _f32c(projmatrix), _f32c(campos), _f32c(rs.bg)
@@ -253,23 +255,50 @@ class _RasterizeBlurry(torch.autograd.Function):
         # blurred = sum_s color_s / denom: its gradient is folded in by the kernel (dL_dblur argument)
         gb = _f32c(grad_blur) if grad_blur is not None else None
         gd = _f32c(grad_depth) if grad_depth is not None else None
-        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj) = _backward_batched(
+        holder = ctx.stats_holder
+        (dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, stats) = _backward_batched(
             P, F, M, ctx.num_rendered, means3D, sh, colors_c, opac, scales, rot, cov, view, proj, campos, bg,
             rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
-            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D, gb, ctx.denom)
+            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D, gb, ctx.denom,
+            holder is not None)
+        if holder is not None:
+            holder.fill(stats, F)
         return (dmeans3D, dmeans2D, dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
-                dview, dproj, None, None, None)
+                dview, dproj, None, None, None, None)
+
+
+class DensificationStats:
+    """Filled by the backward pass of `rasterize_blurry`: per Gaussian, over the sub-frames of the view,
+    sum of |dL/dmeans2D[:, :2]| where visible, number of visible sub-frames, and max screen radius --
+    exactly what the reference's training loop accumulates sub-frame by sub-frame (train.py:188-193,
+    scene/gaussian_model.py:456-458), without materialising or re-reading the [F,P,3] gradient."""
+
+    def __init__(self):
+        self.grad_norm_sum = None    # [P,1]
+        self.visible_count = None    # [P,1]
+        self.max_radius = None       # [P] int32
+        self.num_subframes = 0
+
+    def fill(self, stats, F):
+        self.grad_norm_sum = stats[:, 0:1]
+        self.visible_count = stats[:, 1:2]
+        self.max_radius = stats[:, 2].to(torch.int32)
+        self.num_subframes = F
+
+    @property
+    def ready(self):
+        return self.grad_norm_sum is not None
 
 
 def rasterize_blurry(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                     viewmatrix, projmatrix, campos, raster_settings, blur_denominator=None):
+                     viewmatrix, projmatrix, campos, raster_settings, blur_denominator=None, stats_holder=None):
     empty = torch.Tensor([])
     return _RasterizeBlurry.apply(
         means3D, means2D, sh if sh is not None else empty,
         colors_precomp if colors_precomp is not None else empty, opacities,
         scales if scales is not None else empty, rotations if rotations is not None else empty,
         cov3Ds_precomp if cov3Ds_precomp is not None else empty,
-        viewmatrix, projmatrix, campos, raster_settings, blur_denominator)
+        viewmatrix, projmatrix, campos, raster_settings, blur_denominator, stats_holder)
 
 
 class GaussianRasterizer(nn.Module):

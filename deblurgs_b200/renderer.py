@@ -8,7 +8,8 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_blurry
+from .rasterizer import (DensificationStats, GaussianRasterizationSettings, GaussianRasterizer,
+                         rasterize_blurry)
 
 
 def render(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, override_color=None, *_compat):
@@ -106,12 +107,14 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
         debug=False,
     )
     shs = pc.get_features if override_color is None else None
+    stats = DensificationStats()   # filled by the backward pass
     color, depth, radii, blurred = rasterize_blurry(
         xyz, screenspace_points, shs, override_color, pc.get_opacity, pc.get_scaling, pc.get_rotation, None,
-        world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator)
+        world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator, stats)
     return {"render": color,
             "depth": depth,
             "blurred": blurred,
             "viewspace_points": screenspace_points,
             "visibility_filter": radii > 0,
-            "radii": radii}
+            "radii": radii,
+            "densification": stats}

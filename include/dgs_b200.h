@@ -95,6 +95,9 @@ int dgs_blur_forward(
  * Per-sub-frame outputs:
  *   dL_dmeans2D [F,P,3] (x,y = gradient w.r.t. NDC, z = 0; reference backward.cu:628-629) or NULL
  *   dL_dviewmatrix [F,16], dL_dprojmatrix [F,16]  (reference quirks reproduced)
+ * densify_stats [P,3] or NULL: per Gaussian (sum over its visible sub-frames of |dL_dmeans2D.xy|, number of
+ * sub-frames in which it is visible, max screen radius) -- the quantities the reference's training loop
+ * accumulates per sub-frame (train.py:188-193, scene/gaussian_model.py:456-458), produced in the same pass.
  * `scratch` must hold dgs_blur_backward_scratch_bytes(P,F) bytes; contents undefined on return.
  */
 size_t dgs_blur_backward_scratch_bytes(int P, int F);
@@ -113,7 +116,7 @@ int dgs_blur_backward(
     char* scratch,
     float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
-    float* dL_dviewmatrix, float* dL_dprojmatrix, void* stream);
+    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats, void* stream);
 
 /* Single-view pair: the reference's rasterize_gaussians / rasterize_gaussians_backward
  * (same argument meaning; F = 1 instance of the batched pair). */

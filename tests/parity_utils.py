@@ -89,8 +89,9 @@ def ours_backward(cam, scene, bg, view, proj, campos, fw, dL_dpix, dL_ddepth, sh
     out = rz._backward_batched(P, F, M, fw["num_rendered"], scene.means3D, shs, colors_precomp, scene.opacities,
                                scales, rots, cov3D_precomp, view, proj, campos, bg, cam.height, cam.width,
                                cam.tanfovx, cam.tanfovy, scale_modifier, 0.2, 100.0, sh_degree, use_sigmoid,
-                               fw["radii"], fw["geom"], fw["binning"], fw["img"], dL_dpix, dL_ddepth, True)
-    return dict(zip(names, out))
+                               fw["radii"], fw["geom"], fw["binning"], fw["img"], dL_dpix, dL_ddepth, True,
+                               want_stats=True)
+    return dict(zip(names + ["densify_stats"], out))
 
 
 def rel_err(a, b, floor_frac=1e-3):

@@ -391,3 +391,55 @@ def test_full_size_properties_c2():
 def test_public_api_blurry_query_and_smoke():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_fused_densification_statistics_match_reference_loop():
+    """The statistics the backward kernel emits == the reference's per-sub-frame loop (train.py:188-193,
+    gaussian_model.py:456-458) evaluated on the per-sub-frame radii and means2D gradients."""
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("small")
+    F, W, H, P = view.shape[0], cam.width, cam.height, scene.means3D.shape[0]
+    fw = pu.ours_forward(cam, scene, bg, view, proj, campos)
+    g = torch.Generator().manual_seed(11)
+    dpix = (torch.randn(F, 3, H, W, generator=g) / (H * W)).cuda()
+    b = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix, torch.zeros(F, 1, H, W).cuda())
+    accum = torch.zeros(P, 1).cuda()
+    denom = torch.zeros(P, 1).cuda()
+    max_r = torch.zeros(P).cuda()
+    for s in range(F):
+        vis = fw["radii"][s] > 0
+        max_r[vis] = torch.max(max_r[vis], fw["radii"][s][vis].float())
+        accum[vis] += torch.norm(b["dL_dmeans2D"][s][vis, :2], dim=-1, keepdim=True)
+        denom[vis] += 1.0 / F
+    st = b["densify_stats"]
+    assert torch.allclose(st[:, 0:1], accum, rtol=1e-5, atol=1e-12)
+    assert torch.allclose(st[:, 1:2] / F, denom, rtol=1e-6)
+    assert torch.equal(st[:, 2], max_r)
+
+
+def test_query_public_api_and_densification_holder():
+    import bench
+    dev = torch.device("cuda", 0)
+    w = bench.build_workload("small", 0, dev)
+    cmm, gs = w["cmm"], w["gaussians"]
+    out = cmm.query(0, "all", background=w["bg"])
+    F = w["F"]
+    assert out["subframes"].shape == (F, 3, w["H"], w["W"]) and out["depths"].shape == (F, 1, w["H"], w["W"])
+    assert len(out["render_pkgs"]) == F and out["render_pkgs"][0]["radii"].shape == (w["P"],)
+    assert (out["blurred"] - out["subframes"].mean(0)).abs().max() <= 1e-6
+    pkg = out["batched"]
+    assert not pkg["densification"].ready
+    loss = (out["blurred"] - w["gt_host"].to(dev)).abs().mean() + 1e-3 * (out["subframes"][1:] - out["subframes"][:-1]).abs().mean()
+    loss.backward()
+    assert pkg["densification"].ready and pkg["viewspace_points"].grad.shape == (F, w["P"], 3)
+    gs.add_densification_stats_blurry(pkg)
+    ref_accum = torch.zeros_like(gs.xyz_gradient_accum)
+    for s in range(F):
+        vis = pkg["visibility_filter"][s]
+        ref_accum[vis] += torch.norm(pkg["viewspace_points"].grad[s][vis, :2], dim=-1, keepdim=True)
+    assert torch.allclose(gs.xyz_gradient_accum, ref_accum, rtol=1e-5, atol=1e-12)
+    for prm in gs.parameters() + cmm.parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all()
+    # single sub-frame query before curve_start_iter (train.py:127-130): always nu[0] (scene/motion.py:129-131)
+    one = cmm.query(0, 1, background=w["bg"])
+    assert one["subframes"].shape[0] == 1
+    assert (one["subframes"][0] - out["subframes"][0]).abs().max() <= 1e-6
