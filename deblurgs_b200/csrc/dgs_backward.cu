@@ -134,16 +134,10 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
     if (half == 0 && (int)e < qn) {
         const float A = g0.z, B = g0.w, Cc = g1.x, o = g1.y;
         float* rec = reinterpret_cast<float*>(grad_s + __float_as_uint(g1.z));
-        atomicAdd(rec + 0, -(A * Sx + B * Sy) * ddelx_dx);
-        atomicAdd(rec + 1, -(Cc * Sy + B * Sx) * ddely_dy);
-        atomicAdd(rec + 2, -0.5f * Sxx);
-        atomicAdd(rec + 3, -0.5f * Sxy);
-        atomicAdd(rec + 4, -0.5f * Syy);
-        atomicAdd(rec + 5, o != 0.f ? S0 / o : 0.f);
-        atomicAdd(rec + 6, Cd);
-        atomicAdd(rec + 7, Cr);
-        atomicAdd(rec + 8, Cg);
-        atomicAdd(rec + 9, Cb);
+        // three 16-B vector reductions per 48-B record (sm_90+ red.global.add.v4.f32) instead of ten scalar ones
+        red_add_v4(rec + 0, -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy, -0.5f * Sxx, -0.5f * Sxy);
+        red_add_v4(rec + 4, -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, Cr);
+        red_add_v4(rec + 8, Cg, Cb, 0.f, 0.f);
     }
     __syncwarp();
 }
