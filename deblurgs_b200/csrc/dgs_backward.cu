@@ -10,13 +10,15 @@
 // shared last-row term; quaternion and scale gradients ignore normalisation / scale_modifier.
 //
 // Design differences (B200-first): the reference issues 10 global float atomics per
-// contributing (pixel, Gaussian) pair.  Here a warp first reduces the 10 components over its
-// 32 pixels with a 12-shuffle halving exchange (each step trades half of the remaining
-// components with the partner lane), which leaves the 10 totals in 10 distinct lanes; those
-// lanes then issue ONE warp-wide RED into a 48-B AoS gradient record.  The per-Gaussian
-// stage is one kernel (the reference has two) whose threads loop over the F sub-frames and
-// keep the Gaussian's parameter gradients in registers, writing them once per blurry view;
-// view/projection-matrix gradients are warp-reduced the same way and accumulated in fp64.
+// contributing (pixel, Gaussian) pair.  Here the blend backward queues, per warp, the two
+// per-pixel scalars of every contributing list entry in shared memory and lets each lane
+// accumulate one queued entry's gradient moments over the warp's pixels (k_render_bwd below),
+// ending in three 16-B vector REDs per (warp, Gaussian) into a 48-B AoS gradient record.  The
+// per-Gaussian stage is one kernel (the reference has two) whose threads loop over the F
+// sub-frames and keep the Gaussian's parameter gradients in registers, writing them once per
+// blurry view; view/projection-matrix gradients (21 values per sub-frame) are reduced over the
+// warp with a 23-shuffle halving exchange (each step trades half of the remaining components
+// with the partner lane) and accumulated in fp64.
 #include "dgs_internal.cuh"
 
 namespace dgs {

@@ -156,7 +156,8 @@ int dgs_backward(
  * reference's per-sub-frame quantities (GeometryState / BinningState / ImageState,
  * rasterizer_impl.h:31-63).  All outputs optional (NULL = skip).
  *   depths [F,P] means2D [F,P,2] conic_opacity [F,P,4] rgb [F,P,3] clamped [F,P,3]
- *   tiles_touched [F,P] u32   point_offsets [F,P] u32 (inclusive scan over the whole batch)
+ *   tiles_touched [F,P] u32   point_offsets [F*P] u32 (inclusive scan of tiles_touched over the whole batch
+ *   taken in the library's depth-sorted entry order; its last element is num_rendered)
  */
 int dgs_debug_geometry(const char* geom_buffer, int P, int F,
                        float* depths, float* means2D, float* conic_opacity, float* rgb,
