@@ -112,7 +112,7 @@ class RefCamera:
 def build_workload(config, rank, device):
     from deblurgs_b200 import synthetic
     from deblurgs_b200.motion import CameraMotionModule, GaussianParams
-    P, W, H, F, order = synthetic.CONFIGS[config]
+    P, W, H, F, order = synthetic.get_config(config)
     cam = synthetic.make_camera(W, H)
     scene = synthetic.make_scene(P, cam, seed=0).to(device)            # same Gaussians on every rank
     traj = synthetic.make_trajectory(F, order, seed=1 + rank).to(device)  # one view per rank
@@ -261,7 +261,7 @@ def cpu_baseline(config_name, seconds_budget=25.0):
     import numpy as np
     from deblurgs_b200 import synthetic
     from oracle import pose_torch as pt, raster_np as rn
-    P, W, H, F, order = synthetic.CONFIGS[config_name]
+    P, W, H, F, order = synthetic.get_config(config_name)
     cam = synthetic.make_camera(W, H)
     scene = synthetic.make_scene(P, cam, seed=0)
     traj = synthetic.make_trajectory(F, order, seed=1)

@@ -23,6 +23,15 @@ CONFIGS = {
 }
 
 
+def get_config(name):
+    """(P, W, H, F, curve_order) of a named config, or of an ad-hoc "P=<n>,F=<n>[,W=<n>,H=<n>,C=<n>]" string
+    (sweep points of BASELINE.json config 5; defaults are c2's image size and curve order)."""
+    if name in CONFIGS:
+        return CONFIGS[name]
+    kv = dict(item.split("=") for item in name.split(","))
+    return (int(kv["P"]), int(kv.get("W", 600)), int(kv.get("H", 400)), int(kv["F"]), int(kv.get("C", 9)))
+
+
 @dataclass
 class Camera:
     """Pinhole intrinsics shared by all sub-frames (scene/motion.py:178 uses original_cam[0])."""
