@@ -443,3 +443,32 @@ def test_query_public_api_and_densification_holder():
     one = cmm.query(0, 1, background=w["bg"])
     assert one["subframes"].shape[0] == 1
     assert (one["subframes"][0] - out["subframes"][0]).abs().max() <= 1e-6
+
+
+def test_mark_visible_and_render_dropin_forms():
+    """dgs_mark_visible == the reference's in_frustum test (auxiliary.h:144-169: view-space z > 0.2), and
+    `render` accepts both the reference signature and the upstream-3DGS one with `pipe`."""
+    import math
+    import deblurgs_b200 as dg
+    from deblurgs_b200.motion import GaussianParams, MiniCam
+    cam, scene, traj, bg, view, proj, campos = pu.make_inputs("tiny")
+    rs = dg.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, bg, 1.0, 0.2, 100.0, False, 3,
+                                          campos[0], False, False)
+    vis = dg.GaussianRasterizer(rs).markVisible(scene.means3D, view[0], proj[0])
+    m = torch.cat([scene.means3D, torch.ones_like(scene.means3D[:, :1])], 1)
+    z = (m @ view[0])[:, 2]                       # row-vector convention: p_view = [p,1] @ world_view_transform
+    assert vis.dtype == torch.bool and torch.equal(vis, z > 0.2)
+    pc = GaussianParams.from_scene(scene)
+    mc = MiniCam(cam.width, cam.height, cam.fovy, cam.fovx, 0.01, 100.0, view[1], proj[1], campos[1])
+    a = dg.render(mc, pc, bg)
+    b = dg.render(mc, pc, object(), bg)           # upstream form: third positional argument is `pipe`
+    assert set(a) == {"render", "depth", "viewspace_points", "visibility_filter", "radii"}
+    assert torch.equal(a["render"], b["render"]) and a["render"].shape == (3, cam.height, cam.width)
+    col = torch.rand(scene.means3D.shape[0], 3, device="cuda")
+    c = dg.render(mc, pc, bg, 1.0, col)            # override_color -> colors_precomp path
+    assert torch.isfinite(c["render"]).all() and not torch.equal(c["render"], a["render"])
+    a["render"].sum().backward()
+    assert a["viewspace_points"].grad is not None and a["viewspace_points"].grad.shape == scene.means3D.shape
+    # MiniCam without an explicit centre falls back to the reference's matrix inverse
+    mc2 = MiniCam(cam.width, cam.height, cam.fovy, cam.fovx, 0.01, 100.0, view[1], proj[1])
+    assert (mc2.camera_center - campos[1]).abs().max() <= 1e-5
