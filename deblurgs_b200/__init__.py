@@ -12,6 +12,7 @@ from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rast
 from .renderer import render, render_blurry
 from .pose import bezier_se3_poses
 from .knn import distCUDA2
+from .loss import blur_photometric_loss
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_blurry",
-           "render", "render_blurry", "bezier_se3_poses", "distCUDA2"]
+           "render", "render_blurry", "bezier_se3_poses", "distCUDA2", "blur_photometric_loss"]

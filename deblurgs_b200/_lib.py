@@ -48,6 +48,8 @@ SIGNATURES = {
     "dgs_debug_workload": (_i, [_p, _p, _p, _i, _i, _i, _i, _i64, _p, _p]),
     "dgs_pose_forward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_pose_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dgs_blur_loss_forward": (_i, [_i, _i64, _p, _p, _p, _f, _p, _p, _p]),
+    "dgs_blur_loss_backward": (_i, [_i, _i64, _p, _p, _p, _f, _p, _p, _p, _p]),
     "dgs_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
     "dgs_knn_scratch_bytes": (C.c_size_t, [_i]),
     "dgs_knn_mean_dist2": (_i, [_i, _p, _p, _p, _p]),

@@ -1,0 +1,115 @@
+// Fused photometric loss of the blurry-view training step and its gradient.
+//
+// Reference behaviour restated here (taekkii/deblurgs):
+//   Ll1        = l1_loss(blur, gt)                       utils/loss_utils.py:17-18, train.py:147
+//   L_t_smooth = batchwise_smoothness_loss(subframes)    utils/loss_utils.py:80-93, train.py:148
+//              = mean |subframes[1:] - subframes[:-1]|   (0 when there is a single sub-frame)
+//   loss       = Ll1 + lambda_t_smooth * L_t_smooth      train.py:160-163 (photometric part)
+// The reference evaluates this with ~8 elementwise / reduction launches over the [F,3,H,W] stack
+// forward and as many backward; here one kernel reads every sub-frame pixel once and produces both
+// sums, and one kernel writes dL/dblurred and dL/dsubframes (sign() = 0 at 0, like torch.abs).
+#include "dgs_b200.h"
+#include "dgs_internal.cuh"
+
+namespace dgs {
+
+__global__ void __launch_bounds__(256) k_blur_loss_fwd(int F, size_t chw, const float* __restrict__ sub,
+                                                       const float* __restrict__ blur,
+                                                       const float* __restrict__ gt, double* __restrict__ sums)
+{
+    double a1 = 0.0, a2 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += (size_t)gridDim.x * blockDim.x) {
+        a1 += (double)fabsf(blur[i] - gt[i]);
+        float prev = sub[i];
+        float acc = 0.f;
+        for (int s = 1; s < F; s++) {
+            const float cur = sub[(size_t)s * chw + i];
+            acc += fabsf(cur - prev);
+            prev = cur;
+        }
+        a2 += (double)acc;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+    }
+    __shared__ double s1[8], s2[8];
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a1; s2[threadIdx.x >> 5] = a2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; w++) { t1 += s1[w]; t2 += s2[w]; }
+        atomicAdd(sums, t1);
+        atomicAdd(sums + 1, t2);
+    }
+}
+
+__global__ void k_blur_loss_finalize(int F, size_t chw, float lambda_t, const double* __restrict__ sums,
+                                     float* __restrict__ out)
+{
+    const double l1 = sums[0] / (double)chw;
+    const double sm = F > 1 ? sums[1] / ((double)(F - 1) * (double)chw) : 0.0;
+    out[0] = (float)(l1 + (double)lambda_t * sm);
+    out[1] = (float)l1;
+    out[2] = (float)sm;
+}
+
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(256) k_blur_loss_bwd(int F, size_t chw, const float* __restrict__ sub,
+                                                       const float* __restrict__ blur,
+                                                       const float* __restrict__ gt, float lambda_t,
+                                                       const float* __restrict__ grad_out,
+                                                       float* __restrict__ dblur, float* __restrict__ dsub)
+{
+    const float go = grad_out ? grad_out[0] : 1.0f;
+    const float k1 = go / (float)chw;
+    const float k2 = F > 1 ? go * lambda_t / ((float)(F - 1) * (float)chw) : 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += (size_t)gridDim.x * blockDim.x) {
+        dblur[i] = sgn(blur[i] - gt[i]) * k1;
+        float prev = sub[i];
+        float sprev = 0.f;                       // sign(sub[s] - sub[s-1])
+        for (int s = 0; s < F; s++) {
+            float snext = 0.f, nxt = prev;
+            if (s + 1 < F) {
+                nxt = sub[(size_t)(s + 1) * chw + i];
+                snext = sgn(nxt - prev);
+            }
+            dsub[(size_t)s * chw + i] = (sprev - snext) * k2;
+            sprev = snext;
+            prev = nxt;
+        }
+    }
+}
+
+}  // namespace dgs
+
+extern "C" {
+
+int dgs_blur_loss_forward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
+                          float lambda_t_smooth, float* loss_out, double* scratch, void* stream)
+{
+    if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
+    if (!subframes || !blurred || !gt || !loss_out || !scratch) return DGS_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return DGS_ERR_CUDA;
+    const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
+    dgs::k_blur_loss_fwd<<<blocks, 256, 0, st>>>(F, (size_t)chw, subframes, blurred, gt, scratch);
+    dgs::k_blur_loss_finalize<<<1, 1, 0, st>>>(F, (size_t)chw, lambda_t_smooth, scratch, loss_out);
+    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+}
+
+int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
+                           float lambda_t_smooth, const float* grad_out, float* dL_dblurred,
+                           float* dL_dsubframes, void* stream)
+{
+    if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
+    if (!subframes || !blurred || !gt || !dL_dblurred || !dL_dsubframes) return DGS_ERR_INVALID_ARGUMENT;
+    const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
+    dgs::k_blur_loss_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(F, (size_t)chw, subframes, blurred, gt,
+                                                                    lambda_t_smooth, grad_out, dL_dblurred,
+                                                                    dL_dsubframes);
+    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+}
+
+}  // extern "C"

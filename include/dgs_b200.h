@@ -214,6 +214,19 @@ int dgs_pose_backward(int F, int curve_order,
                       const float* dL_dviewmatrix, const float* dL_dprojmatrix,
                       float* dL_dctrl_trans, float* dL_dctrl_rot, float* dL_dnu, void* stream);
 
+/*
+ * Fused photometric loss of the blurry-view step (reference: train.py:147-163, utils/loss_utils.py:17-18,
+ * 80-93):  loss = mean|blurred - gt| + lambda_t_smooth * mean|subframes[1:] - subframes[:-1]|.
+ *   subframes [F, chw], blurred [chw], gt [chw] (chw = 3*H*W), loss_out [3] = (loss, l1, smoothness),
+ *   scratch [2] doubles.  Backward: grad_out = device pointer to dL/dloss (NULL = 1), writes
+ *   dL_dblurred [chw] and dL_dsubframes [F, chw].
+ */
+int dgs_blur_loss_forward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
+                          float lambda_t_smooth, float* loss_out, double* scratch, void* stream);
+int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
+                           float lambda_t_smooth, const float* grad_out, float* dL_dblurred,
+                           float* dL_dsubframes, void* stream);
+
 /* present [P] uint8: 1 iff view-space z > 0.2 (reference in_frustum, auxiliary.h:144-169). */
 int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

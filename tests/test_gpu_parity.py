@@ -472,3 +472,24 @@ def test_mark_visible_and_render_dropin_forms():
     # MiniCam without an explicit centre falls back to the reference's matrix inverse
     mc2 = MiniCam(cam.width, cam.height, cam.fovy, cam.fovx, 0.01, 100.0, view[1], proj[1])
     assert (mc2.camera_center - campos[1]).abs().max() <= 1e-5
+
+
+def test_fused_photometric_loss_matches_torch():
+    from deblurgs_b200.loss import blur_photometric_loss
+    g = torch.Generator().manual_seed(4)
+    for F in (1, 2, 7):
+        sub = torch.rand(F, 3, 37, 53, generator=g).cuda().requires_grad_(True)
+        sub.data[:, :, :4, :4] = 0.25                      # exact ties: sign(0) = 0 like torch.abs
+        blur = sub.mean(0).detach().clone().requires_grad_(True)
+        gt = torch.rand(3, 37, 53, generator=g).cuda()
+        lam = 0.37
+        ref = (blur - gt).abs().mean() + (lam * (sub[1:] - sub[:-1]).abs().mean() if F > 1 else 0.0)
+        gb_ref, gs_ref = torch.autograd.grad(ref * 1.7, [blur, sub], allow_unused=True)
+        mine = blur_photometric_loss(blur, sub, gt, lam)
+        gb, gs = torch.autograd.grad(mine * 1.7, [blur, sub])
+        assert abs(mine.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+        assert torch.allclose(gb, gb_ref, rtol=1e-5, atol=1e-9)
+        if F > 1:
+            assert torch.allclose(gs, gs_ref, rtol=1e-5, atol=1e-9)
+        else:
+            assert float(gs.abs().max()) == 0.0
