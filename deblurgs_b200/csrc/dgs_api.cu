@@ -43,7 +43,8 @@ static long long g_stage_calls[ST_COUNT];
 static long long g_own_launches = 0;
 static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges",
                                             "render_fwd", "blur_mean", "bwd_memset", "render_bwd",
-                                            "preprocess_bwd", "pose_fwd", "pose_bwd"};
+                                            "preprocess_bwd", "pose_fwd", "pose_bwd", "activate_fwd",
+                                            "activate_bwd", "adam"};
 static cudaEvent_t get_event()
 {
     if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }

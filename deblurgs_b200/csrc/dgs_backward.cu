@@ -205,8 +205,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
     bg_dot_dpixel += f.background[2] * dpix2;
     bg_dot_dpixel += f.z_far * dpixd;
 
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_depth = 0.f;
+    // Suffix sum of the replay (see the loop below): everything behind the current entry, dotted with
+    // dL/dpix.  Behind the last contributor there is only the background.
+    float R = T_final * bg_dot_dpixel;
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
 
     const int rounds = (list_len + DGS_TILE_PIX - 1) / DGS_TILE_PIX;
@@ -255,25 +256,22 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
                 if (!__any_sync(FULL_MASK, contrib)) continue;
                 float w1 = 0.f, w2 = 0.f;
                 if (contrib) {
-                    // one IEEE reciprocal shared by T / (1 - alpha) and -T_final / (1 - alpha) (the
-                    // reference divides twice; <= 1 ulp apart, far inside the gradient tolerance)
-                    const float inv_1ma = 1.0f / (1.f - alpha);
+                    // The reference replays T and the colour accumulated BEHIND the entry as normalised
+                    // recurrences (accum_rec, backward.cu:585-600) and divides twice by (1 - alpha).  The
+                    // same derivative written on un-normalised sums needs one dot product and one
+                    // reciprocal:  with T_i the transmittance in front of entry i, w_j = alpha_j T_j and
+                    // R_i = sum_{j behind i} w_j (c_j . dL/dpix) + T_final (bg . dL/dpix),
+                    //   dL/dalpha_i = T_i (c_i . dL/dpix) - R_i / (1 - alpha_i),   R_{i-1} = R_i + w_i (c_i . dL/dpix).
+                    // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp) is far inside the 1e-3
+                    // gradient tolerance.
+                    const float inv_1ma = rcp_approx(1.f - alpha);
                     T = T * inv_1ma;
                     w2 = alpha * T;
                     const float4 cd = lds_f4(a_rgbd + 16u * (uint32_t)j);
-                    float dL_dalpha = 0.0f;
-                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = cd.x;
-                    dL_dalpha += (cd.x - acc0) * dpix0;
-                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = cd.y;
-                    dL_dalpha += (cd.y - acc1) * dpix1;
-                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = cd.z;
-                    dL_dalpha += (cd.z - acc2) * dpix2;
-                    accd = last_alpha * last_depth + (1.f - last_alpha) * accd; last_depth = cd.w;
-                    dL_dalpha += (cd.w - accd) * dpixd;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-                    w1 = con_o.w * dL_dalpha * G;
+                    const float cdot = cd.x * dpix0 + cd.y * dpix1 + cd.z * dpix2 + cd.w * dpixd;
+                    const float dL_dalpha = T * cdot - R * inv_1ma;
+                    R = fmaf(w2, cdot, R);
+                    w1 = con_o.w * G * dL_dalpha;
                 }
                 sm.qw[warp][qn][lane] = make_float2(w1, w2);
                 if (lane == 0) {

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import renderer
+from .params import FusedAdam, activate_gaussians
 from .pose import bezier_se3_poses
 
 
@@ -65,7 +66,7 @@ class GaussianParams:
     features = cat(dc, rest))."""
 
     def __init__(self, xyz, features_dc, features_rest, scaling, rotation, opacity, active_sh_degree,
-                 z_near=0.2, z_far=100.0, use_sigmoid=False, scale_lower_bound=0.0):
+                 z_near=0.2, z_far=100.0, use_sigmoid=False, scale_lower_bound=0.0, use_isotropic=False):
         self._xyz = nn.Parameter(xyz.contiguous())
         self._features_dc = nn.Parameter(features_dc.contiguous())
         self._features_rest = nn.Parameter(features_rest.contiguous())
@@ -77,6 +78,8 @@ class GaussianParams:
         self.z_far = z_far
         self.use_sigmoid = use_sigmoid
         self.scale_lower_bound = scale_lower_bound
+        self.use_isotropic = use_isotropic
+        self.optimizer = None
 
     @classmethod
     def from_scene(cls, scene, **kw):
@@ -120,12 +123,35 @@ class GaussianParams:
         self.denom += st.visible_count / float(st.num_subframes)
         self.max_radii2D = torch.max(self.max_radii2D, st.max_radius.to(self.max_radii2D.dtype))
 
+    def training_setup(self, position_lr_init=0.00016, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005,
+                       rotation_lr=0.001, spatial_lr_scale=1.0):
+        """The reference's optimizer (scene/gaussian_model.py:175-190: Adam, eps=1e-15, one parameter per
+        named group), stepped by one fused launch (`params.FusedAdam`)."""
+        groups = [
+            {"params": [self._xyz], "lr": position_lr_init * spatial_lr_scale, "name": "xyz"},
+            {"params": [self._features_dc], "lr": feature_lr, "name": "f_dc"},
+            {"params": [self._features_rest], "lr": feature_lr / 20.0, "name": "f_rest"},
+            {"params": [self._opacity], "lr": opacity_lr, "name": "opacity"},
+            {"params": [self._scaling], "lr": scaling_lr, "name": "scaling"},
+            {"params": [self._rotation], "lr": rotation_lr, "name": "rotation"},
+        ]
+        self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        return self.optimizer
+
+    def get_activated(self):
+        """(get_features, get_scaling, get_rotation, get_opacity) from ONE fused launch; what the batched
+        renderer reads once per blurry view."""
+        return activate_gaussians(self._features_dc, self._features_rest, self._scaling, self._rotation,
+                                  self._opacity, self.scale_lower_bound, self.use_isotropic)
+
     @property
     def get_xyz(self):
         return self._xyz
 
     @property
     def get_scaling(self):
+        if self.use_isotropic:
+            return torch.exp(self._scaling[:, :1].expand(-1, 3)) + self.scale_lower_bound
         return torch.exp(self._scaling) + self.scale_lower_bound
 
     @property

@@ -106,10 +106,17 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
         prefiltered=False,
         debug=False,
     )
-    shs = pc.get_features if override_color is None else None
+    if hasattr(pc, "get_activated"):
+        # parameter store with the fused activation kernel (params.activate_gaussians): one launch
+        shs, scales, rotations, opacities = pc.get_activated()
+    else:
+        # any object with the reference's GaussianModel getters
+        shs, scales, rotations, opacities = pc.get_features, pc.get_scaling, pc.get_rotation, pc.get_opacity
+    if override_color is not None:
+        shs = None
     stats = DensificationStats()   # filled by the backward pass
     color, depth, radii, blurred = rasterize_blurry(
-        xyz, screenspace_points, shs, override_color, pc.get_opacity, pc.get_scaling, pc.get_rotation, None,
+        xyz, screenspace_points, shs, override_color, opacities, scales, rotations, None,
         world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator, stats)
     return {"render": color,
             "depth": depth,

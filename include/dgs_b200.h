@@ -227,6 +227,39 @@ int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const flo
                            float lambda_t_smooth, const float* grad_out, float* dL_dblurred,
                            float* dL_dsubframes, void* stream);
 
+/*
+ * Gaussian parameter store, the steps either side of the rasterizer.
+ *
+ * dgs_activate_forward replaces the four getters `render` reads -- get_features (cat of _features_dc
+ * [P,1,3] and _features_rest [P,M-1,3]), get_scaling (exp + scale_lb; isotropic != 0: column 0 expanded),
+ * get_rotation (F.normalize, eps 1e-12), get_opacity (clamp to [0,1]) -- scene/gaussian_model.py:114-137,
+ * scene/gaussian_activation.py:29-52; one launch per blurry view instead of ~8 torch launches per
+ * sub-frame.  dgs_activate_backward is its chain rule; incoming gradients may be NULL (= zero), every
+ * outgoing gradient is written (not accumulated).
+ */
+int dgs_activate_forward(int P, int sh_coeffs, const float* features_dc, const float* features_rest,
+                         const float* scaling, const float* rotation, const float* opacity,
+                         float scale_lower_bound, int isotropic,
+                         float* shs, float* scales, float* rotations, float* opacities, void* stream);
+int dgs_activate_backward(int P, int sh_coeffs, const float* scaling, const float* rotation, const float* opacity,
+                          int isotropic, const float* dL_dshs, const float* dL_dscales, const float* dL_drotations,
+                          const float* dL_dopacities, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+                          float* dL_dscaling, float* dL_drotation, float* dL_dopacity, void* stream);
+
+/*
+ * One Adam step over up to DGS_ADAM_MAX_TENSORS parameter tensors in a single launch: the reference's
+ * `torch.optim.Adam(l, lr=0.0, eps=1e-15)` with one parameter per group and per-group learning rates
+ * (scene/gaussian_model.py:175-190, train.py:204-208; amsgrad / weight decay / maximize off).
+ * HOST arrays of n_tensors entries: device pointers params/grads/exp_avg/exp_avg_sq, numel, lr, and the
+ * 1-based step count of each tensor AFTER this update.  clip_grad_value > 0 clamps each gradient element
+ * to [-clip, clip] on the fly (torch.nn.utils.clip_grad_value_, train.py:204-205; the stored gradient is
+ * left untouched).
+ */
+#define DGS_ADAM_MAX_TENSORS 8
+int dgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, const double* lr, const int64_t* step,
+                  double beta1, double beta2, double eps, double clip_grad_value, void* stream);
+
 /* present [P] uint8: 1 iff view-space z > 0.2 (reference in_frustum, auxiliary.h:144-169). */
 int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

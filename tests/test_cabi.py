@@ -41,7 +41,7 @@ def test_introspection_and_key_bits():
         assert (tb.value, sb.value) == (etb, esb)
     assert lib.dgs_blur_backward_scratch_bytes(1000, 4) >= 1000 * 4 * 48
     assert lib.dgs_knn_scratch_bytes(1000) > 0
-    assert lib.dgs_profile_num_stages() == 12
+    assert lib.dgs_profile_num_stages() == 15
 
 
 def test_argument_validation_happens_before_any_device_work():
@@ -69,6 +69,59 @@ def test_argument_validation_happens_before_any_device_work():
                               one, None, one, one, one, 1.0, 1.0, 0.2, 100.0, 0, 0, one, one, one, None, 1.0,
                               C.byref(n), None)
     assert rc == -3
+
+
+def test_parameter_store_entry_points_validate_arguments():
+    lib = _lib.load()
+    one = C.c_void_p(1)   # never dereferenced: validation fails first
+    # activations: M >= 1, features_rest required iff M > 1, every output required
+    assert lib.dgs_activate_forward(10, 0, one, one, one, one, one, 0.0, 0, one, one, one, one, None) == -1
+    assert lib.dgs_activate_forward(10, 16, one, None, one, one, one, 0.0, 0, one, one, one, one, None) == -1
+    assert lib.dgs_activate_forward(10, 16, one, one, one, one, one, 0.0, 0, None, one, one, one, None) == -1
+    assert lib.dgs_activate_forward(0, 16, None, None, None, None, None, 0.0, 0, None, None, None, None, None) == 0
+    assert lib.dgs_activate_backward(10, 16, one, one, one, 0, None, None, None, None, one, one, one, one, None,
+                                     None) == -1
+    assert lib.dgs_activate_backward(0, 1, None, None, None, 0, None, None, None, None, None, None, None, None,
+                                     None, None) == 0
+    # Adam: at most DGS_ADAM_MAX_TENSORS tensors per launch, 1-based step counts, no null tensors
+    n = 2
+    ptrs = (C.c_void_p * n)(1, 1)
+    numel = (C.c_int64 * n)(8, 8)
+    lr = (C.c_double * n)(0.1, 0.1)
+    step_ok, step_bad = (C.c_int64 * n)(1, 1), (C.c_int64 * n)(1, 0)
+    assert lib.dgs_adam_step(9, ptrs, ptrs, ptrs, ptrs, numel, lr, step_ok, 0.9, 0.999, 1e-15, 0.0, None) == -1
+    assert lib.dgs_adam_step(n, ptrs, ptrs, ptrs, ptrs, numel, lr, step_bad, 0.9, 0.999, 1e-15, 0.0, None) == -1
+    nulls = (C.c_void_p * n)(1, None)
+    assert lib.dgs_adam_step(n, ptrs, nulls, ptrs, ptrs, numel, lr, step_ok, 0.9, 0.999, 1e-15, 0.0, None) == -1
+    assert lib.dgs_adam_step(0, None, None, None, None, None, None, None, 0.9, 0.999, 1e-15, 0.0, None) == 0
+    empty = (C.c_int64 * n)(0, 0)   # nothing to update: no launch, no dereference
+    assert lib.dgs_adam_step(n, ptrs, ptrs, ptrs, ptrs, empty, lr, step_ok, 0.9, 0.999, 1e-15, 0.0, None) == 0
+
+
+def test_fused_adam_host_logic_and_cpu_rejection():
+    from deblurgs_b200.params import FusedAdam, activate_gaussians
+    from deblurgs_b200.motion import GaussianParams
+    P, M = 6, 4
+    g = GaussianParams(torch.zeros(P, 3), torch.zeros(P, 1, 3), torch.zeros(P, M - 1, 3), torch.zeros(P, 3),
+                       torch.ones(P, 4), torch.ones(P, 1), 1)
+    opt = g.training_setup(position_lr_init=0.00016, spatial_lr_scale=2.0)
+    # the reference's six named groups in its order (scene/gaussian_model.py:181-188), Adam eps 1e-15
+    assert [gr["name"] for gr in opt.param_groups] == ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"]
+    assert opt.param_groups[0]["lr"] == 0.00016 * 2.0 and opt.param_groups[2]["lr"] == 0.0025 / 20.0
+    assert all(gr["eps"] == 1e-15 and gr["betas"] == (0.9, 0.999) for gr in opt.param_groups)
+    opt.step()                       # no gradients anywhere: nothing to do, nothing launched
+    assert opt.state == {}
+    g._xyz.grad = torch.ones(P, 3)
+    with pytest.raises(_lib.DgsError, match="no CPU path"):
+        opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert g._xyz.grad is None
+    sd = opt.state_dict()
+    assert [gr["params"] for gr in sd["param_groups"]] == [[0], [1], [2], [3], [4], [5]]
+    with pytest.raises(_lib.DgsError, match="no CPU path"):
+        activate_gaussians(g._features_dc, g._features_rest, g._scaling, g._rotation, g._opacity)
+    plain = FusedAdam([torch.zeros(3, requires_grad=True)], lr=0.5)
+    assert plain.param_groups[0]["lr"] == 0.5 and plain.param_groups[0]["eps"] == 1e-8
 
 
 def test_missing_library_fails_loudly(monkeypatch):
