@@ -85,57 +85,78 @@ struct HalvingReduce {
 //   phase 1 (lane = pixel): replay the list back to front exactly like the reference and, for
 //           every entry with a contributing pixel, append ONE column to a per-warp queue in
 //           shared memory: per pixel the two scalars w1 = opacity*G*dL/dalpha and w2 = alpha*T
-//           (zeros where the pixel does not contribute), plus the entry's (xy, conic, opacity,
-//           record offset).
+//           (zeros where the pixel does not contribute), plus the entry's Gaussian index.
 //   phase 2 (lane = queued entry, when 16 entries are queued): each lane walks the pixels of
-//           the rectangle (two half-warps take 16 pixels each), accumulates the six moments
-//           sum w1*{1,dx,dy,dx^2,dx*dy,dy^2} and sum w2*dL/dpix{r,g,b,depth} in registers with
-//           every lane busy, converts them to the 10 gradient components and issues the REDs.
-// All sums are over the same terms as the reference's; only their order differs.
+//           the rectangle (two half-warps take 16 pixels each), accumulates the moments
+//           sum w1*{1,px,py,px^2,px*py} about the rectangle's corner and sum w2*dL/dpix{r,g,b,depth}
+//           in registers with every lane busy, shifts the moments to the Gaussian's centre
+//           (= sum w1*{1,dx,dy,dx^2,dx*dy,dy^2}), converts them to the 10 gradient components and
+//           issues the REDs.
+// The sums are the reference's, regrouped.
 // ---------------------------------------------------------------------------------------
 #define BWD_QN 16                 // queued entries per flush
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
 
 struct BwdSmem {
-    uint32_t off[DGS_TILE_PIX];
+    uint32_t id[DGS_TILE_PIX];           // Gaussian index of the staged entry
     float2 xy[DGS_TILE_PIX];
     float4 con[DGS_TILE_PIX];
     float4 rgbd[DGS_TILE_PIX];
     float2 qw[8][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
-    float4 qg0[8][BWD_QN];               // x, y, conic.x, conic.y
-    float4 qg1[8][BWD_QN];               // conic.z, opacity, record offset (bits), -
+    uint32_t qid[8][BWD_QN];             // per warp: Gaussian index of the queued entry
     float4 dpix[8][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
     int tile_max;
 };
 
+// Phase 2.  Lane (e, half) owns queued entry e and the 16 pixels of rows 2*half, 2*half+1 of the warp's
+// 8x4 rectangle.  The weighted moments are accumulated about the rectangle's corner with the pixel
+// offsets as compile-time constants (sum w, sum w*px, sum w*px^2, ...; py is 0 or 1), and shifted to the
+// Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
+// until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the staging
+// pass fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
 __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned lane, int qn, float wx0f,
-                                          float wy0f, float ddelx_dx, float ddely_dy, char* __restrict__ grad_s)
+                                          float wy0f, float ddelx_dx, float ddely_dy,
+                                          const float4* __restrict__ geo0, const float4* __restrict__ geo1,
+                                          char* __restrict__ grad_s)
 {
     __syncwarp();
     const unsigned e = lane & 15u, half = lane >> 4;
-    const float4 g0 = sm.qg0[warp][e];
-    const float4 g1 = sm.qg1[warp][e];
-    // pixel p = half*16 + pp of the 8x4 rectangle: x = wx0 + (p & 7), y = wy0 + (p >> 3)
-    const float bx = g0.x - wx0f, by = g0.y - (wy0f + 2.0f * (float)half);
-    float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
+    const bool live = (int)e < qn;
+    uint32_t id = 0;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (live) {
+        id = sm.qid[warp][e];
+        g0 = __ldg(geo0 + id);   // x, y, depth, radius
+        g1 = __ldg(geo1 + id);   // conic a, b, c, opacity
+    }
+    float M0 = 0.f, Mx = 0.f, My = 0.f, Mxx = 0.f, Mxy = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
 #pragma unroll
     for (int pp = 0; pp < 16; pp++) {
         const float2 w = sm.qw[warp][e][half * 16 + pp];
         const float4 dp = sm.dpix[warp][half * 16 + pp];
-        const float dx = bx - (float)(pp & 7), dy = by - (float)(pp >> 3);
-        const float tx = w.x * dx, ty = w.x * dy;
-        S0 += w.x; Sx += tx; Sy += ty;
-        Sxx += tx * dx; Sxy += tx * dy; Syy += ty * dy;
-        Cr += w.y * dp.x; Cg += w.y * dp.y; Cb += w.y * dp.z; Cd += w.y * dp.w;
+        const float px = (float)(pp & 7);
+        M0 += w.x;
+        Mx = fmaf(w.x, px, Mx);
+        Mxx = fmaf(w.x, px * px, Mxx);
+        if (pp >= 8) { My += w.x; Mxy = fmaf(w.x, px, Mxy); }   // py = 1 (py^2 = py: Myy = My)
+        Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
     }
+    // shift to the centre: pixel (px, py) of this half is at distance (bx - px, by - py) from it
+    const float bx = g0.x - wx0f, by = g0.y - (wy0f + 2.0f * (float)half);
+    float S0 = M0;
+    float Sx = bx * M0 - Mx;
+    float Sy = by * M0 - My;
+    float Sxx = bx * (bx * M0 - 2.0f * Mx) + Mxx;
+    float Sxy = bx * (by * M0 - My) - by * Mx + Mxy;
+    float Syy = by * (by * M0 - 2.0f * My) + My;
     S0 += __shfl_xor_sync(FULL_MASK, S0, 16);   Sx += __shfl_xor_sync(FULL_MASK, Sx, 16);
     Sy += __shfl_xor_sync(FULL_MASK, Sy, 16);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, 16);
     Sxy += __shfl_xor_sync(FULL_MASK, Sxy, 16); Syy += __shfl_xor_sync(FULL_MASK, Syy, 16);
     Cr += __shfl_xor_sync(FULL_MASK, Cr, 16);   Cg += __shfl_xor_sync(FULL_MASK, Cg, 16);
     Cb += __shfl_xor_sync(FULL_MASK, Cb, 16);   Cd += __shfl_xor_sync(FULL_MASK, Cd, 16);
-    if (half == 0 && (int)e < qn) {
-        const float A = g0.z, B = g0.w, Cc = g1.x, o = g1.y;
-        float* rec = reinterpret_cast<float*>(grad_s + __float_as_uint(g1.z));
+    if (half == 0 && live) {
+        const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
+        float* rec = reinterpret_cast<float*>(grad_s + (size_t)id * 48u);
         // three 16-B vector reductions per 48-B record (sm_90+ red.global.add.v4.f32) instead of ten scalar ones
         red_add_v4(rec + 0, -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy, -0.5f * Sxx, -0.5f * Sxy);
         red_add_v4(rec + 4, -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, Cr);
@@ -164,6 +185,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     const uint2 range = p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile];
     const uint32_t a_xy = smem_addr(sm.xy), a_con = smem_addr(sm.con), a_rgbd = smem_addr(sm.rgbd);
+    const uint32_t a_id = smem_addr(sm.id);
 
     const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
     const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
@@ -221,7 +243,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
             const uint32_t id = p.point_list[range.x + list_len - progress - 1];
             const float4 a = geo0[id];
             const float4 c = geo2[id];
-            sm.off[tid] = id * 48u;
+            sm.id[tid] = id;
             sm.xy[tid] = make_float2(a.x, a.y);
             sm.con[tid] = geo1[id];
             sm.rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
@@ -243,16 +265,15 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
                 const float2 xy = lds_f2(a_xy + 8u * (uint32_t)j);
                 const float4 con_o = lds_f4(a_con + 16u * (uint32_t)j);
                 const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                bool contrib = false;
                 float G = 0.f, alpha = 0.f;
                 if (inside && contributor < last_contributor) {
                     const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
                     if (power <= 0.0f) {
                         G = expf(power);
                         alpha = min(0.99f, con_o.w * G);
-                        contrib = alpha >= 1.0f / 255.0f;
                     }
                 }
+                const bool contrib = alpha >= 1.0f / 255.0f;
                 if (!__any_sync(FULL_MASK, contrib)) continue;
                 float w1 = 0.f, w2 = 0.f;
                 if (contrib) {
@@ -274,18 +295,15 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
                     w1 = con_o.w * G * dL_dalpha;
                 }
                 sm.qw[warp][qn][lane] = make_float2(w1, w2);
-                if (lane == 0) {
-                    sm.qg0[warp][qn] = make_float4(xy.x, xy.y, con_o.x, con_o.y);
-                    sm.qg1[warp][qn] = make_float4(con_o.z, con_o.w, __uint_as_float(sm.off[j]), 0.f);
-                }
+                sm.qid[warp][qn] = lds_u32(a_id + 4u * (uint32_t)j);   // same value from every lane
                 if (++qn == BWD_QN) {
-                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, grad_s);
+                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, grad_s);
                     qn = 0;
                 }
             }
         }
     }
-    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, grad_s);
+    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, grad_s);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
