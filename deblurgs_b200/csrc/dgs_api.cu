@@ -391,7 +391,7 @@ int dgs_blur_backward(
         DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
     }
     if (num_rendered > 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
-    { StageTimer t(ST_PREPROCESS_BWD, st, 2); launch_preprocess_bwd(b, sh_degree, st); }
+    { StageTimer t(ST_PREPROCESS_BWD, st, colors_precomp ? 2 : 3); launch_preprocess_bwd(b, sh_degree, st); }
     DGS_CUDA(cudaGetLastError(), "backward launch");
     return DGS_OK;
 }

@@ -94,6 +94,8 @@ struct HalvingReduce {
 //           issues the REDs.
 // The sums are the reference's, regrouped.
 // ---------------------------------------------------------------------------------------
+#define BWD_WARPS 4               // warps per block: a block owns a 16 x (4*BWD_WARPS/2) strip of a tile
+#define BWD_THREADS (32 * BWD_WARPS)
 #define BWD_QN 16                 // queued entries per flush
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
 
@@ -102,9 +104,9 @@ struct BwdSmem {
     float2 xy[DGS_TILE_PIX];
     float4 con[DGS_TILE_PIX];
     float4 rgbd[DGS_TILE_PIX];
-    float2 qw[8][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
-    uint32_t qid[8][BWD_QN];             // per warp: Gaussian index of the queued entry
-    float4 dpix[8][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
+    float2 qw[BWD_WARPS][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
+    uint32_t qid[BWD_WARPS][BWD_QN];             // per warp: Gaussian index of the queued entry
+    float4 dpix[BWD_WARPS][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
     int tile_max;
 };
 
@@ -165,17 +167,23 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __restrict__ grad)
+__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, float* __restrict__ grad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
 
     const FwdParams& f = p.f;
     const int s = blockIdx.z;
-    const int tile = blockIdx.y * f.tiles_x + blockIdx.x;
+    // blockIdx.y = tile row * BWD_STRIPS + strip: the 8 / BWD_WARPS strips of a tile are separate blocks that
+    // walk the same tile list.  Fewer warps per barrier (the warps of a block wait for the one with the
+    // most surviving entries every staged batch), and each strip replays only up to ITS deepest contributor.
+    constexpr unsigned BWD_STRIPS = 8 / BWD_WARPS, STRIP_H = DGS_TILE_Y / BWD_STRIPS;
+    const unsigned tile_y = blockIdx.y / BWD_STRIPS, strip = blockIdx.y % BWD_STRIPS;
+    const int tile = tile_y * f.tiles_x + blockIdx.x;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31, warp = tid >> 5;
-    const unsigned wx0 = blockIdx.x * DGS_TILE_X + (warp & 1) * 8, wy0 = blockIdx.y * DGS_TILE_Y + (warp >> 1) * 4;
+    const unsigned wx0 = blockIdx.x * DGS_TILE_X + (warp & 1) * 8;
+    const unsigned wy0 = tile_y * DGS_TILE_Y + strip * STRIP_H + (warp >> 1) * 4;
     const unsigned pixx = wx0 + (lane & 7), pixy = wy0 + (lane >> 3);
     const float rx0 = (float)wx0, ry0 = (float)wy0, rx1 = (float)(wx0 + 7), ry1 = (float)(wy0 + 3);
     const bool inside = pixx < (unsigned)f.W && pixy < (unsigned)f.H;
@@ -238,15 +246,19 @@ __global__ void __launch_bounds__(256) k_render_bwd(const BwdParams p, float* __
 
     for (int i = 0; i < rounds; i++, todo -= DGS_TILE_PIX) {
         __syncthreads();
-        const int progress = i * DGS_TILE_PIX + tid;
-        if (progress < list_len) {
-            const uint32_t id = p.point_list[range.x + list_len - progress - 1];
-            const float4 a = geo0[id];
-            const float4 c = geo2[id];
-            sm.id[tid] = id;
-            sm.xy[tid] = make_float2(a.x, a.y);
-            sm.con[tid] = geo1[id];
-            sm.rgbd[tid] = make_float4(c.x, c.y, c.z, a.z);
+#pragma unroll
+        for (int k = 0; k < DGS_TILE_PIX / BWD_THREADS; k++) {
+            const int slot = k * BWD_THREADS + tid;
+            const int progress = i * DGS_TILE_PIX + slot;
+            if (progress < list_len) {
+                const uint32_t id = p.point_list[range.x + list_len - progress - 1];
+                const float4 a = geo0[id];
+                const float4 c = geo2[id];
+                sm.id[slot] = id;
+                sm.xy[slot] = make_float2(a.x, a.y);
+                sm.con[slot] = geo1[id];
+                sm.rgbd[slot] = make_float4(c.x, c.y, c.z, a.z);
+            }
         }
         __syncthreads();
         const int batch = min(DGS_TILE_PIX, todo);
@@ -315,7 +327,7 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
         cudaFuncSetAttribute(k_render_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
         configured = true;
     }
-    dim3 grid(f.tiles_x, f.tiles_y, f.F), block(DGS_TILE_PIX);
+    dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
     k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p, reinterpret_cast<float*>(p.g0));
 }
 
@@ -323,13 +335,18 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 // per-Gaussian backward: cov2D, projection, SH and cov3D stages for all F sub-frames.
 // ---------------------------------------------------------------------------------------
 #define NPOSE 21
+#define BWD_PF 3    // prefetch depth of the per-Gaussian backward (iterations ahead)
+#define PRE_BWD_THREADS 128
 // pose component order: view {0,1,2,4,5,6,8,9,10,12,13,14} -> 0..11, proj {0,1,4,5,8,9,12,13}
 // -> 12..19, proj last-row term (entries 3,7,11,15) -> 20
 __device__ static const int kPoseSlot[NPOSE] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14,
                                                 16, 17, 20, 21, 24, 25, 28, 29, 19};
 
-template <int DEG>
-__global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const float* __restrict__ grad)
+// Geometry half (cov2D / EWA, projection of the mean, cov3D -> scale / rotation, view / projection-matrix
+// gradients, densification statistics).  PRECOMP: colours were supplied precomputed, their gradient
+// is a plain sum over sub-frames and rides along here; otherwise the SH half (k_sh_bwd) handles colour.
+template <bool PRECOMP>
+__global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdParams p, const float* __restrict__ grad)
 {
     const FwdParams& f = p.f;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,19 +367,6 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
         cov3d_from_scale_rot(scale.x, scale.y, scale.z, f.scale_modifier, q, cov3D);
     }
 
-    constexpr int NC = DEG >= 0 ? (DEG + 1) * (DEG + 1) : 1;
-    float sh[NC][3];
-    float dsh[NC][3];
-#pragma unroll
-    for (int k = 0; k < NC; k++) { dsh[k][0] = dsh[k][1] = dsh[k][2] = 0.f; sh[k][0] = sh[k][1] = sh[k][2] = 0.f; }
-    if (DEG >= 0) {
-        const float* src = f.shs + (size_t)gi * f.M * 3;
-#pragma unroll
-        for (int k = 0; k < NC; k++) {
-            sh[k][0] = __ldg(src + 3 * k); sh[k][1] = __ldg(src + 3 * k + 1); sh[k][2] = __ldg(src + 3 * k + 2);
-        }
-    }
-
     float3 dmean = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dopac = 0.f;
@@ -372,32 +376,39 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     const int my_comp = HalvingReduce<NPOSE>::owner(lane);
     const int my_slot = my_comp >= 0 ? kPoseSlot[my_comp] : -1;
 
-    // Software pipeline: the per-(sub-frame, Gaussian) record of iteration s+1 (radius, 48-B gradient,
-    // clamp mask) is requested while iteration s computes.  The kernel runs at one 256-thread block
-    // per SM (register-limited), so without this every iteration exposes a full DRAM round trip.
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int nx_radius = 0;
-    float4 nx_a = zero4, nx_b = zero4, nx_c = zero4;
-    unsigned nx_mask = 0;
+    // Software pipeline, BWD_PF iterations deep: the per-(sub-frame, Gaussian) record (radius, 48-B
+    // gradient, clamp mask) of iteration s+BWD_PF is requested while iteration s computes.  The kernel
+    // runs at one 256-thread block per SM (register-limited), so the bytes in flight per SM are
+    // warps x lanes x 56 B x depth: depth 1 left the SM at ~1/3 of what HBM latency x bandwidth needs.
+    // All five loads of a stage are independent (the gradient record of an invisible entry is the
+    // zero-fill, its mask is never used), so no stage waits for its own radius.
+    struct Stage { int radius; float4 a, b; float2 c; };
     auto fetch = [&](int s) {
+        Stage t;
         const size_t n = (size_t)s * f.P + gi;
-        nx_radius = live ? f.radii[n] : 0;
-        if (nx_radius > 0) {
-            nx_a = reinterpret_cast<const float4*>(grad)[n * 3];
-            nx_b = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
-            nx_c = reinterpret_cast<const float4*>(grad)[n * 3 + 2];
-            nx_mask = __float_as_uint(reinterpret_cast<const float*>(f.geo2 + n)[3]);
-        }
+        t.radius = live ? f.radii[n] : 0;
+        t.a = reinterpret_cast<const float4*>(grad)[n * 3];
+        t.b = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
+        t.c = PRECOMP ? reinterpret_cast<const float2*>(grad)[n * 6 + 4] : make_float2(0.f, 0.f);
+        return t;
     };
-    if (f.F > 0) fetch(0);
+    Stage pf[BWD_PF];
+#pragma unroll
+    for (int k = 0; k < BWD_PF; k++) {
+        pf[k].radius = 0;
+        if (k < f.F) pf[k] = fetch(k);
+    }
 
     for (int s = 0; s < f.F; s++) {
         const size_t n = (size_t)s * f.P + gi;
-        const bool vis = nx_radius > 0;
-        const int nx_radius_cur = nx_radius;
-        const float4 ga = nx_a, gb = nx_b, gc = nx_c;
-        const unsigned cur_mask = nx_mask;
-        if (s + 1 < f.F) fetch(s + 1);
+        const Stage cur = pf[0];
+#pragma unroll
+        for (int k = 0; k + 1 < BWD_PF; k++) pf[k] = pf[k + 1];
+        if (s + BWD_PF < f.F) pf[BWD_PF - 1] = fetch(s + BWD_PF);
+        const bool vis = cur.radius > 0;
+        const int nx_radius_cur = cur.radius;
+        const float4 ga = cur.a, gb = cur.b;
+        const float2 gc = cur.c;
         if (p.dL_dmeans2D != nullptr && live) {
             p.dL_dmeans2D[n * 3] = vis ? ga.x : 0.f;
             p.dL_dmeans2D[n * 3 + 1] = vis ? ga.y : 0.f;
@@ -496,114 +507,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
             // depth part of the view-matrix gradient (backward.cu:454-457)
             pv[2] += ddepth * mean.x; pv[5] += ddepth * mean.y; pv[8] += ddepth * mean.z; pv[11] += ddepth;
 
-            // ---- colour: SH backward (reference backward.cu:20-140) or precomputed colour
-            if (DEG >= 0) {
-                const float3 cam = {f.campos[3 * s], f.campos[3 * s + 1], f.campos[3 * s + 2]};
-                const float3 dir_orig = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
-                const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-                const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-                const unsigned mask = cur_mask;
-                float dRGB[3] = {dcol.x, dcol.y, dcol.z};
-                if (f.use_sigmoid) {
-                    // recompute the pre-activation colour
-                    float pre[3];
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) pre[ch] = kSH0 * sh[0][ch];
-                    if (DEG > 0) {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++)
-                            pre[ch] = pre[ch] - kSH1 * y * sh[1][ch] + kSH1 * z * sh[2][ch] - kSH1 * x * sh[3][ch];
-                        if (DEG > 1) {
-                            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-                            for (int ch = 0; ch < 3; ch++)
-                                pre[ch] = pre[ch] + kSH2[0] * xy * sh[4][ch] + kSH2[1] * yz * sh[5][ch] +
-                                          kSH2[2] * (2.0f * zz - xx - yy) * sh[6][ch] + kSH2[3] * xz * sh[7][ch] +
-                                          kSH2[4] * (xx - yy) * sh[8][ch];
-                            if (DEG > 2) {
-#pragma unroll
-                                for (int ch = 0; ch < 3; ch++)
-                                    pre[ch] = pre[ch] + kSH3[0] * y * (3.0f * xx - yy) * sh[9][ch] +
-                                              kSH3[1] * xy * z * sh[10][ch] +
-                                              kSH3[2] * y * (4.0f * zz - xx - yy) * sh[11][ch] +
-                                              kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12][ch] +
-                                              kSH3[4] * x * (4.0f * zz - xx - yy) * sh[13][ch] +
-                                              kSH3[5] * z * (xx - yy) * sh[14][ch] +
-                                              kSH3[6] * x * (xx - 3.0f * yy) * sh[15][ch];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        const float sg = 1.0f / (1.0f + expf(-pre[ch]));
-                        dRGB[ch] *= sg * (1.0f - sg);
-                    }
-                } else {
-                    dRGB[0] *= (mask & 1u) ? 1.f : 0.f;
-                    dRGB[1] *= (mask & 2u) ? 1.f : 0.f;
-                    dRGB[2] *= (mask & 4u) ? 1.f : 0.f;
-                }
-                float dRGBdx[3] = {0.f, 0.f, 0.f}, dRGBdy[3] = {0.f, 0.f, 0.f}, dRGBdz[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) dsh[0][ch] += kSH0 * dRGB[ch];
-                if (DEG > 0) {
-                    const float b1 = -kSH1 * y, b2 = kSH1 * z, b3 = -kSH1 * x;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        dsh[1][ch] += b1 * dRGB[ch]; dsh[2][ch] += b2 * dRGB[ch]; dsh[3][ch] += b3 * dRGB[ch];
-                        dRGBdx[ch] = -kSH1 * sh[3][ch]; dRGBdy[ch] = -kSH1 * sh[1][ch]; dRGBdz[ch] = kSH1 * sh[2][ch];
-                    }
-                    if (DEG > 1) {
-                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                        const float b4 = kSH2[0] * xy, b5 = kSH2[1] * yz, b6 = kSH2[2] * (2.f * zz - xx - yy);
-                        const float b7 = kSH2[3] * xz, b8 = kSH2[4] * (xx - yy);
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) {
-                            dsh[4][ch] += b4 * dRGB[ch]; dsh[5][ch] += b5 * dRGB[ch]; dsh[6][ch] += b6 * dRGB[ch];
-                            dsh[7][ch] += b7 * dRGB[ch]; dsh[8][ch] += b8 * dRGB[ch];
-                            dRGBdx[ch] += kSH2[0] * y * sh[4][ch] + kSH2[2] * 2.f * -x * sh[6][ch] + kSH2[3] * z * sh[7][ch] + kSH2[4] * 2.f * x * sh[8][ch];
-                            dRGBdy[ch] += kSH2[0] * x * sh[4][ch] + kSH2[1] * z * sh[5][ch] + kSH2[2] * 2.f * -y * sh[6][ch] + kSH2[4] * 2.f * -y * sh[8][ch];
-                            dRGBdz[ch] += kSH2[1] * y * sh[5][ch] + kSH2[2] * 2.f * 2.f * z * sh[6][ch] + kSH2[3] * x * sh[7][ch];
-                        }
-                        if (DEG > 2) {
-                            const float b9 = kSH3[0] * y * (3.f * xx - yy), b10 = kSH3[1] * xy * z;
-                            const float b11 = kSH3[2] * y * (4.f * zz - xx - yy);
-                            const float b12 = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                            const float b13 = kSH3[4] * x * (4.f * zz - xx - yy), b14 = kSH3[5] * z * (xx - yy);
-                            const float b15 = kSH3[6] * x * (xx - 3.f * yy);
-#pragma unroll
-                            for (int ch = 0; ch < 3; ch++) {
-                                dsh[9][ch] += b9 * dRGB[ch]; dsh[10][ch] += b10 * dRGB[ch]; dsh[11][ch] += b11 * dRGB[ch];
-                                dsh[12][ch] += b12 * dRGB[ch]; dsh[13][ch] += b13 * dRGB[ch]; dsh[14][ch] += b14 * dRGB[ch];
-                                dsh[15][ch] += b15 * dRGB[ch];
-                                dRGBdx[ch] += (kSH3[0] * sh[9][ch] * 3.f * 2.f * xy + kSH3[1] * sh[10][ch] * yz +
-                                               kSH3[2] * sh[11][ch] * -2.f * xy + kSH3[3] * sh[12][ch] * -3.f * 2.f * xz +
-                                               kSH3[4] * sh[13][ch] * (-3.f * xx + 4.f * zz - yy) +
-                                               kSH3[5] * sh[14][ch] * 2.f * xz + kSH3[6] * sh[15][ch] * 3.f * (xx - yy));
-                                dRGBdy[ch] += (kSH3[0] * sh[9][ch] * 3.f * (xx - yy) + kSH3[1] * sh[10][ch] * xz +
-                                               kSH3[2] * sh[11][ch] * (-3.f * yy + 4.f * zz - xx) +
-                                               kSH3[3] * sh[12][ch] * -3.f * 2.f * yz + kSH3[4] * sh[13][ch] * -2.f * xy +
-                                               kSH3[5] * sh[14][ch] * -2.f * yz + kSH3[6] * sh[15][ch] * -3.f * 2.f * xy);
-                                dRGBdz[ch] += (kSH3[1] * sh[10][ch] * xy + kSH3[2] * sh[11][ch] * 4.f * 2.f * yz +
-                                               kSH3[3] * sh[12][ch] * 3.f * (2.f * zz - xx - yy) +
-                                               kSH3[4] * sh[13][ch] * 4.f * 2.f * xz + kSH3[5] * sh[14][ch] * (xx - yy));
-                            }
-                        }
-                    }
-                }
-                const float3 dL_ddir = {dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2],
-                                        dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2],
-                                        dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2]};
-                // gradient through the normalisation of the view direction
-                const float3 vv = dir_orig;
-                const float sum2 = vv.x * vv.x + vv.y * vv.y + vv.z * vv.z;
-                const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-                dm.x += ((+sum2 - vv.x * vv.x) * dL_ddir.x - vv.y * vv.x * dL_ddir.y - vv.z * vv.x * dL_ddir.z) * invsum32;
-                dm.y += (-vv.x * vv.y * dL_ddir.x + (sum2 - vv.y * vv.y) * dL_ddir.y - vv.z * vv.y * dL_ddir.z) * invsum32;
-                dm.z += (-vv.x * vv.z * dL_ddir.x - vv.y * vv.z * dL_ddir.y + (sum2 - vv.z * vv.z) * dL_ddir.z) * invsum32;
-            } else {
-                dcolor_acc.x += dcol.x; dcolor_acc.y += dcol.y; dcolor_acc.z += dcol.z;
-            }
+            if (PRECOMP) { dcolor_acc.x += dcol.x; dcolor_acc.y += dcol.y; dcolor_acc.z += dcol.z; }
             dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
         }
         // pose gradients of this sub-frame: warp reduce, then fp64 atomics
@@ -617,12 +521,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     if (p.densify_stats != nullptr) {
         p.densify_stats[3 * g] = st_norm; p.densify_stats[3 * g + 1] = st_count; p.densify_stats[3 * g + 2] = (float)st_radius;
     }
-    if (DEG >= 0) {
-        float* dst = p.dL_dsh + (size_t)g * f.M * 3;
-#pragma unroll
-        for (int k = 0; k < NC; k++) { dst[3 * k] = dsh[k][0]; dst[3 * k + 1] = dsh[k][1]; dst[3 * k + 2] = dsh[k][2]; }
-        for (int k = NC; k < f.M; k++) { dst[3 * k] = 0.f; dst[3 * k + 1] = 0.f; dst[3 * k + 2] = 0.f; }
-    } else if (p.dL_dcolors_precomp) {
+    if (PRECOMP && p.dL_dcolors_precomp) {
         p.dL_dcolors_precomp[3 * g] = dcolor_acc.x; p.dL_dcolors_precomp[3 * g + 1] = dcolor_acc.y;
         p.dL_dcolors_precomp[3 * g + 2] = dcolor_acc.z;
     }
@@ -673,6 +572,179 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(const BwdParams p, const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Colour half of the per-Gaussian backward: spherical harmonics (reference backward.cu:20-140).
+// Thread = Gaussian, loop over the F sub-frames, dL/dsh accumulated in registers and written once.
+// The Gaussian's own coefficients are parked in shared memory (one float4 column per thread) and
+// streamed through the loop instead of living in 48 more registers: with the geometry half split
+// off, this runs at 4 blocks of 128 threads per SM instead of one 256-thread block, which is what a
+// latency-bound kernel needs (the fused version sat at 2 warps per scheduler, 33 % issue slots busy).
+// The view-direction gradient uses  dL/ddir = sum_k (sh_k . dL/dRGB) grad b_k(dir): one dot product
+// per coefficient instead of three derivative accumulations per channel (same terms, regrouped).
+// Adds its dL/dmean contribution to the value the geometry half wrote (stream order).
+// ---------------------------------------------------------------------------------------
+#define SH_BWD_THREADS 128
+
+template <int DEG>
+__global__ void __launch_bounds__(SH_BWD_THREADS) k_sh_bwd(const BwdParams p, const float* __restrict__ grad)
+{
+    const FwdParams& f = p.f;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = g < f.P;
+    const int gi = live ? g : 0;
+    constexpr int NC = (DEG + 1) * (DEG + 1);
+    constexpr int NV = (3 * NC + 3) / 4;          // float4 slots per Gaussian
+    __shared__ float4 s_sh[NV][SH_BWD_THREADS];
+
+    const float3 mean = {f.means3D[3 * gi], f.means3D[3 * gi + 1], f.means3D[3 * gi + 2]};
+    {
+        const float* src = f.shs + (size_t)gi * f.M * 3;
+        float tmp[4 * NV];
+#pragma unroll
+        for (int k = 0; k < 4 * NV; k++) tmp[k] = k < 3 * NC ? __ldg(src + k) : 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            s_sh[v][threadIdx.x] = make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]);
+    }
+    // only this thread reads its column back: no barrier needed
+    const uint32_t a_sh = smem_addr(&s_sh[0][threadIdx.x]);
+    // coefficient k, channel ch = float 3k+ch of the column; SHV(v) re-reads float4 slot v (volatile: the
+    // compiler must not hoist the 48 values back into registers)
+#define SHV(v) lds_f4(a_sh + (uint32_t)(v) * (uint32_t)(SH_BWD_THREADS * 16))
+
+    float dsh[NC][3];
+#pragma unroll
+    for (int k = 0; k < NC; k++) dsh[k][0] = dsh[k][1] = dsh[k][2] = 0.f;
+    float3 dmean = {0.f, 0.f, 0.f};
+
+    struct Stage { int radius; float cr, cg, cb; unsigned mask; };
+    auto fetch = [&](int s) {
+        Stage t;
+        const size_t n = (size_t)s * f.P + gi;
+        t.radius = live ? f.radii[n] : 0;
+        t.cr = grad[n * 12 + 7]; t.cg = grad[n * 12 + 8]; t.cb = grad[n * 12 + 9];
+        t.mask = __float_as_uint(reinterpret_cast<const float*>(f.geo2 + n)[3]);
+        return t;
+    };
+    Stage pf[BWD_PF];
+#pragma unroll
+    for (int k = 0; k < BWD_PF; k++) {
+        pf[k].radius = 0;
+        if (k < f.F) pf[k] = fetch(k);
+    }
+
+    for (int s = 0; s < f.F; s++) {
+        const Stage cur = pf[0];
+#pragma unroll
+        for (int k = 0; k + 1 < BWD_PF; k++) pf[k] = pf[k + 1];
+        if (s + BWD_PF < f.F) pf[BWD_PF - 1] = fetch(s + BWD_PF);
+        if (cur.radius <= 0) continue;
+
+        const float3 cam = {f.campos[3 * s], f.campos[3 * s + 1], f.campos[3 * s + 2]};
+        const float3 vv = {mean.x - cam.x, mean.y - cam.y, mean.z - cam.z};
+        const float len = sqrtf(vv.x * vv.x + vv.y * vv.y + vv.z * vv.z);
+        const float x = vv.x / len, y = vv.y / len, z = vv.z / len;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+
+        // basis values b_k(dir), in the reference's expression order
+        float bs[NC];
+        bs[0] = kSH0;
+        if (DEG > 0) { bs[1] = -kSH1 * y; bs[2] = kSH1 * z; bs[3] = -kSH1 * x; }
+        if (DEG > 1) {
+            bs[4] = kSH2[0] * xy; bs[5] = kSH2[1] * yz; bs[6] = kSH2[2] * (2.f * zz - xx - yy);
+            bs[7] = kSH2[3] * xz; bs[8] = kSH2[4] * (xx - yy);
+        }
+        if (DEG > 2) {
+            bs[9] = kSH3[0] * y * (3.f * xx - yy); bs[10] = kSH3[1] * xy * z;
+            bs[11] = kSH3[2] * y * (4.f * zz - xx - yy); bs[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+            bs[13] = kSH3[4] * x * (4.f * zz - xx - yy); bs[14] = kSH3[5] * z * (xx - yy);
+            bs[15] = kSH3[6] * x * (xx - 3.f * yy);
+        }
+
+        float dRGB[3] = {cur.cr, cur.cg, cur.cb};
+        if (f.use_sigmoid) {
+            // colour = sigmoid(pre): recompute the pre-activation value (reference stores it, forward.cu:72-76);
+            // one pass over the coefficient stream (float i of the column = coefficient i/3, channel i%3)
+            float pre[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int v4 = 0; v4 < NV; v4++) {
+                const float4 q = SHV(v4);
+                const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = 4 * v4 + j;
+                    if (i < 3 * NC) pre[i % 3] = fmaf(bs[i / 3], e[j], pre[i % 3]);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float sg = 1.0f / (1.0f + expf(-pre[ch]));
+                dRGB[ch] *= sg * (1.0f - sg);
+            }
+        } else {
+            dRGB[0] *= (cur.mask & 1u) ? 1.f : 0.f;
+            dRGB[1] *= (cur.mask & 2u) ? 1.f : 0.f;
+            dRGB[2] *= (cur.mask & 4u) ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            dsh[k][0] = fmaf(bs[k], dRGB[0], dsh[k][0]);
+            dsh[k][1] = fmaf(bs[k], dRGB[1], dsh[k][1]);
+            dsh[k][2] = fmaf(bs[k], dRGB[2], dsh[k][2]);
+        }
+        if (DEG > 0) {
+            // v_k = sh_k . dL/dRGB, accumulated while the coefficient stream passes (one float4 live at a
+            // time);  dL/ddir = sum_k v_k grad b_k
+            float v[NC];
+#pragma unroll
+            for (int k = 0; k < NC; k++) v[k] = 0.f;
+#pragma unroll
+            for (int v4 = 0; v4 < NV; v4++) {
+                const float4 q = SHV(v4);
+                const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = 4 * v4 + j;
+                    if (i >= 3 && i < 3 * NC) v[i / 3] = fmaf(e[j], dRGB[i % 3], v[i / 3]);
+                }
+            }
+            float dx = -kSH1 * v[3], dy = -kSH1 * v[1], dz = kSH1 * v[2];
+            if (DEG > 1) {
+                dx += kSH2[0] * y * v[4] + kSH2[2] * 2.f * -x * v[6] + kSH2[3] * z * v[7] + kSH2[4] * 2.f * x * v[8];
+                dy += kSH2[0] * x * v[4] + kSH2[1] * z * v[5] + kSH2[2] * 2.f * -y * v[6] + kSH2[4] * 2.f * -y * v[8];
+                dz += kSH2[1] * y * v[5] + kSH2[2] * 2.f * 2.f * z * v[6] + kSH2[3] * x * v[7];
+            }
+            if (DEG > 2) {
+                dx += kSH3[0] * v[9] * 3.f * 2.f * xy + kSH3[1] * v[10] * yz + kSH3[2] * v[11] * -2.f * xy +
+                      kSH3[3] * v[12] * -3.f * 2.f * xz + kSH3[4] * v[13] * (-3.f * xx + 4.f * zz - yy) +
+                      kSH3[5] * v[14] * 2.f * xz + kSH3[6] * v[15] * 3.f * (xx - yy);
+                dy += kSH3[0] * v[9] * 3.f * (xx - yy) + kSH3[1] * v[10] * xz +
+                      kSH3[2] * v[11] * (-3.f * yy + 4.f * zz - xx) + kSH3[3] * v[12] * -3.f * 2.f * yz +
+                      kSH3[4] * v[13] * -2.f * xy + kSH3[5] * v[14] * -2.f * yz + kSH3[6] * v[15] * -3.f * 2.f * xy;
+                dz += kSH3[1] * v[10] * xy + kSH3[2] * v[11] * 4.f * 2.f * yz +
+                      kSH3[3] * v[12] * 3.f * (2.f * zz - xx - yy) + kSH3[4] * v[13] * 4.f * 2.f * xz +
+                      kSH3[5] * v[14] * (xx - yy);
+            }
+            // gradient through the normalisation of the view direction (reference dnormvdv, auxiliary.h)
+            const float sum2 = vv.x * vv.x + vv.y * vv.y + vv.z * vv.z;
+            const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            dmean.x += ((+sum2 - vv.x * vv.x) * dx - vv.y * vv.x * dy - vv.z * vv.x * dz) * invsum32;
+            dmean.y += (-vv.x * vv.y * dx + (sum2 - vv.y * vv.y) * dy - vv.z * vv.y * dz) * invsum32;
+            dmean.z += (-vv.x * vv.z * dx - vv.y * vv.z * dy + (sum2 - vv.z * vv.z) * dz) * invsum32;
+        }
+    }
+#undef SHV
+    if (!live) return;
+    float* dst = p.dL_dsh + (size_t)g * f.M * 3;
+#pragma unroll
+    for (int k = 0; k < NC; k++) { dst[3 * k] = dsh[k][0]; dst[3 * k + 1] = dsh[k][1]; dst[3 * k + 2] = dsh[k][2]; }
+    for (int k = NC; k < f.M; k++) { dst[3 * k] = 0.f; dst[3 * k + 1] = 0.f; dst[3 * k + 2] = 0.f; }
+    if (DEG > 0) {
+        p.dL_dmeans3D[3 * g] += dmean.x; p.dL_dmeans3D[3 * g + 1] += dmean.y; p.dL_dmeans3D[3 * g + 2] += dmean.z;
+    }
+}
+
 // pose_acc [F,32] fp64 -> dL_dview [F,16], dL_dproj [F,16] fp32
 __global__ void k_pose_finalize(const double* __restrict__ acc, int F, float* __restrict__ dview,
                                 float* __restrict__ dproj)
@@ -694,16 +766,18 @@ void launch_preprocess_bwd(const BwdParams& p, int sh_degree, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.P > 0 && f.F > 0) {
-        dim3 grid((f.P + 255) / 256), block(256);
         const float* grad = reinterpret_cast<const float*>(p.g0);
+        dim3 grid((f.P + PRE_BWD_THREADS - 1) / PRE_BWD_THREADS), block(PRE_BWD_THREADS);
         if (f.colors_precomp != nullptr) {
-            k_preprocess_bwd<-1><<<grid, block, 0, st>>>(p, grad);
+            k_preprocess_bwd<true><<<grid, block, 0, st>>>(p, grad);
         } else {
+            k_preprocess_bwd<false><<<grid, block, 0, st>>>(p, grad);
+            dim3 sgrid((f.P + SH_BWD_THREADS - 1) / SH_BWD_THREADS), sblock(SH_BWD_THREADS);
             switch (sh_degree) {
-                case 0: k_preprocess_bwd<0><<<grid, block, 0, st>>>(p, grad); break;
-                case 1: k_preprocess_bwd<1><<<grid, block, 0, st>>>(p, grad); break;
-                case 2: k_preprocess_bwd<2><<<grid, block, 0, st>>>(p, grad); break;
-                default: k_preprocess_bwd<3><<<grid, block, 0, st>>>(p, grad); break;
+                case 0: k_sh_bwd<0><<<sgrid, sblock, 0, st>>>(p, grad); break;
+                case 1: k_sh_bwd<1><<<sgrid, sblock, 0, st>>>(p, grad); break;
+                case 2: k_sh_bwd<2><<<sgrid, sblock, 0, st>>>(p, grad); break;
+                default: k_sh_bwd<3><<<sgrid, sblock, 0, st>>>(p, grad); break;
             }
         }
     }
