@@ -8,15 +8,21 @@ Mirrors, for curve_type == "se3" (the reference default, arguments/__init__.py:4
   GaussianModel getters       scene/gaussian_model.py:114-137, scene/gaussian_activation.py:29-52
 The sub-frame loop of `query` is replaced by ONE batched render (`renderer.render_blurry`) and the
 pose chain by the on-device generator (`pose.bezier_se3_poses`); names, arguments and the returned
-dictionary keep the reference's meaning. Dataset loading, se3_log initialisation from COLMAP poses,
-save/load and the quaternion curve type are outside the hot path and not provided.
+dictionary keep the reference's meaning. Also provided: initialisation of the
+control points from camera poses (`from_poses`, the reference's `_set_initial_parameters` with
+`se3_log_map`), `add_training_setup`, and curve_type == "quarternion_cartesian" (roma-free quaternion
+algebra in `pose.py`; pose chain in torch, rendering on the same batched kernels). Dataset loading and
+save/load are outside the hot path and not provided.
 """
+import math
+
 import torch
 import torch.nn as nn
 
 from . import renderer
 from .params import FusedAdam, activate_gaussians
-from .pose import bezier_se3_poses
+from .pose import (bezier_se3_poses, c2w_to_minicam_tensors, rotmat_to_unitquat, se3_log_map,
+                   unitquat_to_rotmat)
 
 
 def inverse_sigmoid(x):
@@ -58,6 +64,15 @@ class BezierModel(nn.Module):
 
     def __len__(self):
         return self._control_points.shape[0]
+
+    def forward(self, t, idx):
+        """[f] -> [f, d]: sum_k binom(C,k) t^(C-k) (1-t)^k ctrl[idx, k] in torch (scene/bezier.py:54-83; fp64
+        like the reference, whose binomials are fp64). The se3 curve type does this inside the pose kernel."""
+        C_ = self.curve_order
+        binom = torch.tensor([float(math.comb(C_, k)) for k in range(C_ + 1)], dtype=torch.float64, device=t.device)
+        k = torch.arange(C_ + 1, device=t.device)
+        coeff = (t[:, None] ** (C_ - k)) * ((1 - t)[:, None] ** k) * binom
+        return (coeff[:, :, None] * self._control_points[idx][None]).sum(dim=1)
 
 
 class GaussianParams:
@@ -176,19 +191,60 @@ class CameraMotionModule:
     """
 
     def __init__(self, cameras, initial_se3, curve_order=9, num_subframes=21, curve_random_sample=False,
-                 generator=None):
+                 generator=None, curve_type="se3"):
+        """initial_se3: [n,6] for curve_type "se3"; for "quarternion_cartesian" a tuple
+        (unit quaternions [n,4] XYZW, camera positions [n,3]) (use `from_poses` to build either)."""
         self.curve_order = curve_order
         self.n_subframes = num_subframes
-        self.curve_type = "se3"
+        self.curve_type = curve_type
         self.curve_random_sample = curve_random_sample
         self.gaussians = None
         self.original_cam = cameras
-        self._trans = BezierModel(initial_se3[:, :3], curve_order, generator=generator)
-        self._rot = BezierModel(initial_se3[:, 3:], curve_order, generator=generator)
+        if curve_type == "se3":
+            self._trans = BezierModel(initial_se3[:, :3], curve_order, generator=generator)
+            self._rot = BezierModel(initial_se3[:, 3:], curve_order, generator=generator)
+        elif curve_type == "quarternion_cartesian":
+            quats, positions = initial_se3
+            self._rot = BezierModel(quats, curve_order, generator=generator)
+            self._trans = BezierModel(positions, curve_order, initial_noise=0.01, generator=generator)
+            initial_se3 = positions
+        else:
+            raise NotImplementedError(curve_type)
         n, f = initial_se3.shape[0], num_subframes
         nu0 = torch.linspace(1 / (f - 1), 1.0 - (1 / (f - 1)), f - 2) if f > 2 else torch.zeros(0)
         self._nu = nn.Parameter(inverse_sigmoid(nu0)[None, :].repeat(n, 1).to(initial_se3.device).contiguous()
                                 .requires_grad_(True))
+
+    @classmethod
+    def from_poses(cls, cameras, rotations, translations, curve_type="se3", **kw):
+        """The reference's constructor path (scene/motion.py:36-49, 180-207): `rotations` [n,3,3] are the
+        c2w rotations (CameraInfo.R), `translations` [n,3] the camera positions (-T @ R^T). se3: control
+        points start at se3_log_map of the transposed c2w matrix; quaternion: at (unit quaternion, position)."""
+        n = rotations.shape[0]
+        if curve_type == "se3":
+            c2w = torch.zeros(n, 4, 4, dtype=rotations.dtype, device=rotations.device)
+            c2w[:, :3, :3] = rotations.transpose(-2, -1)
+            c2w[:, 3, :3] = translations
+            c2w[:, 3, 3] = 1.0
+            init = se3_log_map(c2w)
+        elif curve_type == "quarternion_cartesian":
+            init = (rotmat_to_unitquat(rotations), translations)
+        else:
+            raise NotImplementedError(curve_type)
+        return cls(cameras, init, curve_type=curve_type, **kw)
+
+    def add_training_setup(self, gaussians, lr_dict):
+        """Append the curve parameters to the Gaussians' optimizer as groups 'curve_rot', 'curve_trans',
+        'curve_alignment', replacing earlier curve groups and their state (scene/motion.py:63-77)."""
+        opt = gaussians.optimizer
+        for group in opt.param_groups:
+            if "curve_" in group["name"] and group["params"][0] in opt.state:
+                del opt.state[group["params"][0]]
+        opt.param_groups = [e for e in opt.param_groups if "curve_" not in e["name"]]
+        opt.add_param_group({"params": [self._rot._control_points], "lr": lr_dict["curve_rot"], "name": "curve_rot"})
+        opt.add_param_group({"params": [self._trans._control_points], "lr": lr_dict["curve_trans"],
+                             "name": "curve_trans"})
+        opt.add_param_group({"params": [self._nu], "lr": lr_dict["curve_alignment"], "name": "curve_alignment"})
 
     def __len__(self):
         return len(self._trans)
@@ -216,6 +272,11 @@ class CameraMotionModule:
         if nu is None:
             nu = self._sample_nu_from_alignment(idx)
         ref_cam = self.original_cam[0]
+        if self.curve_type == "quarternion_cartesian":
+            # scene/motion.py:242-246: Bezier in quaternion components, renormalised, positions in R^3
+            q = self._rot(nu, idx)
+            q = q / q.norm(dim=1, keepdim=True)
+            return c2w_to_minicam_tensors(unitquat_to_rotmat(q), self._trans(nu, idx), ref_cam.projection_matrix)
         return bezier_se3_poses(self._trans._control_points[idx], self._rot._control_points[idx], nu,
                                 ref_cam.projection_matrix)
 
