@@ -279,6 +279,11 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
                 const float dx = xy.x - pixfx, dy = xy.y - pixfy;
                 float G = 0.f, alpha = 0.f;
                 if (inside && contributor < last_contributor) {
+                    // Exponent and exp() are the forward's (= the reference's), operation for operation: the replay
+                    // must classify every pair exactly as the forward did.  One pair whose alpha falls on the other
+                    // side of 1/255 injects a bogus w * (c . dL/dpix) into R and moves dL/dalpha of EVERY entry in
+                    // front of it at that pixel by up to ~10 % (measured with ex2.approx here: ~100 such pixels per
+                    // c2 view, individual Gaussian gradients off by 2 %, for 0.14 ms) -- not worth it.
                     const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
                     if (power <= 0.0f) {
                         G = expf(power);
