@@ -13,6 +13,8 @@ from .renderer import render, render_blurry
 from .pose import bezier_se3_poses
 from .knn import distCUDA2
 from .loss import blur_photometric_loss
+from .params import FusedAdam, activate_gaussians
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_blurry",
-           "render", "render_blurry", "bezier_se3_poses", "distCUDA2", "blur_photometric_loss"]
+           "render", "render_blurry", "bezier_se3_poses", "distCUDA2", "blur_photometric_loss", "FusedAdam",
+           "activate_gaussians"]
