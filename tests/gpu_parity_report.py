@@ -97,11 +97,16 @@ def report(name, sh_degree=3, use_sigmoid=False, P=None, F=None, do_backward=Tru
                         acc[k] += v.double()
             sums[rep] = acc
         ref, ref2 = sums
-        errs, noise, self_noise = {}, {}, {}
+        errs, noise, self_noise, errs_max = {}, {}, {}, {}
+
+        def relmax(a, b):   # the bar of tests/test_gpu_parity.py: max-abs error over the tensor's max-abs
+            a, b = a.double(), b.double()
+            return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
         pairs = {"dL_dmeans3D": "dL_dmeans3D", "dL_dsh": "dL_dsh", "dL_dopacity": "dL_dopacity",
                  "dL_dscales": "dL_dscales", "dL_drotations": "dL_drotations"}
         for k, rk in pairs.items():
             errs[k] = pu.rel_err(mine[k], ref[rk])
+            errs_max[k] = relmax(mine[k], ref[rk])
             noise[k] = pu.rel_err(ref2[rk], ref[rk])
             self_noise[k] = pu.rel_err(mine2[k], mine[k])
         rv = torch.stack([b["dL_dviewmatrix"] for b in per_s])
@@ -110,7 +115,11 @@ def report(name, sh_degree=3, use_sigmoid=False, P=None, F=None, do_backward=Tru
         errs["dL_dviewmatrix"] = pu.rel_err(mine["dL_dviewmatrix"], rv)
         errs["dL_dprojmatrix"] = pu.rel_err(mine["dL_dprojmatrix"], rp)
         errs["dL_dmeans2D"] = pu.rel_err(mine["dL_dmeans2D"], rm2)
+        errs_max["dL_dviewmatrix"] = relmax(mine["dL_dviewmatrix"], rv)
+        errs_max["dL_dprojmatrix"] = relmax(mine["dL_dprojmatrix"], rp)
+        errs_max["dL_dmeans2D"] = relmax(mine["dL_dmeans2D"], rm2)
         res["grad_rel_err"] = errs
+        res["grad_maxabs_rel_err"] = errs_max
         res["ref_vs_ref_noise"] = noise
         res["ours_vs_ours_noise"] = self_noise
     return res
