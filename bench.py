@@ -41,6 +41,8 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its banner / NCCL_DEBUG output to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
