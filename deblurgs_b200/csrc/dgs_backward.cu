@@ -14,11 +14,12 @@
 // per-pixel scalars of every contributing list entry in shared memory and lets each lane
 // accumulate one queued entry's gradient moments over the warp's pixels (k_render_bwd below),
 // ending in three 16-B vector REDs per (warp, Gaussian) into a 48-B AoS gradient record.  The
-// per-Gaussian stage is one kernel (the reference has two) whose threads loop over the F
-// sub-frames and keep the Gaussian's parameter gradients in registers, writing them once per
-// blurry view; view/projection-matrix gradients (21 values per sub-frame) are reduced over the
-// warp with a 23-shuffle halving exchange (each step trades half of the remaining components
-// with the partner lane) and accumulated in fp64.
+// per-Gaussian stage is two kernels split by register budget, not by the reference's stages --
+// a geometry half (cov2D, projection, cov3D, pose gradients, densification statistics) and an
+// SH half -- whose threads loop over the F sub-frames and keep the Gaussian's parameter
+// gradients in registers, writing them once per blurry view; view/projection-matrix gradients
+// (21 values per sub-frame) are reduced over the warp with a 23-shuffle halving exchange (each
+// step trades half of the remaining components with the partner lane) and accumulated in fp64.
 #include "dgs_internal.cuh"
 
 namespace dgs {
@@ -74,15 +75,17 @@ struct HalvingReduce {
 };
 
 // ---------------------------------------------------------------------------------------
-// tile blending, backward.  grid = (tiles_x, tiles_y, F), 256 threads = one 16x16 tile; each
-// warp owns an 8x4 pixel rectangle and, like the forward, evaluates only the staged entries
-// whose alpha >= 1/255 footprint can reach that rectangle.  grad = AoS float[N][12]:
+// tile blending, backward.  grid = (tiles_x, tiles_y * 8/BWD_WARPS, F), BWD_THREADS threads = one
+// 16 x 8 strip of a tile; each warp owns an 8x4 pixel rectangle and, like the forward, evaluates
+// only the staged entries whose alpha >= 1/255 footprint can reach that rectangle.
+// grad = AoS float[N][12]:
 //   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7,8,9 dcolor | 10,11 unused
 //
 // Gradient accumulation is split in two phases so that no per-entry cross-lane reduction is
 // needed (the reference issues 10 atomics per contributing pixel; a per-entry warp reduction
 // costs ~50 shuffle/select/add instructions per (warp, entry)):
-//   phase 1 (lane = pixel): replay the list back to front exactly like the reference and, for
+//   phase 1 (lane = pixel): replay the list back to front (same pairs, same alpha as the forward;
+//           dL/dalpha from un-normalised suffix sums, see the loop) and, for
 //           every entry with a contributing pixel, append ONE column to a per-warp queue in
 //           shared memory: per pixel the two scalars w1 = opacity*G*dL/dalpha and w2 = alpha*T
 //           (zeros where the pixel does not contribute), plus the entry's Gaussian index.
