@@ -79,7 +79,9 @@ struct HalvingReduce {
 // 16 x 8 strip of a tile; each warp owns an 8x4 pixel rectangle and, like the forward, evaluates
 // only the staged entries whose alpha >= 1/255 footprint can reach that rectangle.
 // grad = AoS float[N][12]:
-//   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7,8,9 dcolor | 10,11 unused
+//   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7 unused | 8,9,10 dcolor | 11 unused
+// (geometry in the first 32-B sector, colour alone in the second: each half of the per-Gaussian backward
+// touches one sector per record)
 //
 // Gradient accumulation is split in two phases so that no per-entry cross-lane reduction is
 // needed (the reference issues 10 atomics per contributing pixel; a per-entry warp reduction
@@ -164,8 +166,8 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
         float* rec = reinterpret_cast<float*>(grad_s + (size_t)id * 48u);
         // three 16-B vector reductions per 48-B record (sm_90+ red.global.add.v4.f32) instead of ten scalar ones
         red_add_v4(rec + 0, -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy, -0.5f * Sxx, -0.5f * Sxy);
-        red_add_v4(rec + 4, -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, Cr);
-        red_add_v4(rec + 8, Cg, Cb, 0.f, 0.f);
+        red_add_v4(rec + 4, -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, 0.f);
+        red_add_v4(rec + 8, Cr, Cg, Cb, 0.f);
     }
     __syncwarp();
 }
@@ -343,7 +345,8 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 // per-Gaussian backward: cov2D, projection, SH and cov3D stages for all F sub-frames.
 // ---------------------------------------------------------------------------------------
 #define NPOSE 21
-#define BWD_PF 3    // prefetch depth of the per-Gaussian backward (iterations ahead)
+#define BWD_PF 3    // prefetch depth of the SH half of the per-Gaussian backward (iterations ahead; register-limited)
+#define GEO_PF 5    // prefetch depth of the geometry half (106 -> ~125 registers, still 4 blocks of 128 threads per SM)
 #define PRE_BWD_THREADS 128
 // pose component order: view {0,1,2,4,5,6,8,9,10,12,13,14} -> 0..11, proj {0,1,4,5,8,9,12,13}
 // -> 12..19, proj last-row term (entries 3,7,11,15) -> 20
@@ -384,25 +387,25 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
     const int my_comp = HalvingReduce<NPOSE>::owner(lane);
     const int my_slot = my_comp >= 0 ? kPoseSlot[my_comp] : -1;
 
-    // Software pipeline, BWD_PF iterations deep: the per-(sub-frame, Gaussian) record (radius, 48-B
-    // gradient, clamp mask) of iteration s+BWD_PF is requested while iteration s computes.  The kernel
-    // runs at one 256-thread block per SM (register-limited), so the bytes in flight per SM are
-    // warps x lanes x 56 B x depth: depth 1 left the SM at ~1/3 of what HBM latency x bandwidth needs.
-    // All five loads of a stage are independent (the gradient record of an invisible entry is the
-    // zero-fill, its mask is never used), so no stage waits for its own radius.
-    struct Stage { int radius; float4 a, b; float2 c; };
+    // Software pipeline, GEO_PF iterations deep: the per-(sub-frame, Gaussian) record (radius, 48-B
+    // gradient, clamp mask) of iteration s+GEO_PF is requested while iteration s computes.  The kernel
+    // is latency-bound (16 warps per SM, 43 % of warp cycles waiting on these loads at depth 3), so the bytes
+    // in flight per SM -- warps x lanes x 36 B x depth -- are what sets its speed.  The loads of a stage are
+    // independent (the gradient record of an invisible entry is the zero-fill), so no stage waits for its
+    // own radius.
+    struct Stage { int radius; float4 a, b, c; };
     auto fetch = [&](int s) {
         Stage t;
         const size_t n = (size_t)s * f.P + gi;
         t.radius = live ? f.radii[n] : 0;
         t.a = reinterpret_cast<const float4*>(grad)[n * 3];
         t.b = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
-        t.c = PRECOMP ? reinterpret_cast<const float2*>(grad)[n * 6 + 4] : make_float2(0.f, 0.f);
+        t.c = PRECOMP ? reinterpret_cast<const float4*>(grad)[n * 3 + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
         return t;
     };
-    Stage pf[BWD_PF];
+    Stage pf[GEO_PF];
 #pragma unroll
-    for (int k = 0; k < BWD_PF; k++) {
+    for (int k = 0; k < GEO_PF; k++) {
         pf[k].radius = 0;
         if (k < f.F) pf[k] = fetch(k);
     }
@@ -411,12 +414,11 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
         const size_t n = (size_t)s * f.P + gi;
         const Stage cur = pf[0];
 #pragma unroll
-        for (int k = 0; k + 1 < BWD_PF; k++) pf[k] = pf[k + 1];
-        if (s + BWD_PF < f.F) pf[BWD_PF - 1] = fetch(s + BWD_PF);
+        for (int k = 0; k + 1 < GEO_PF; k++) pf[k] = pf[k + 1];
+        if (s + GEO_PF < f.F) pf[GEO_PF - 1] = fetch(s + GEO_PF);
         const bool vis = cur.radius > 0;
         const int nx_radius_cur = cur.radius;
-        const float4 ga = cur.a, gb = cur.b;
-        const float2 gc = cur.c;
+        const float4 ga = cur.a, gb = cur.b, gc = cur.c;
         if (p.dL_dmeans2D != nullptr && live) {
             p.dL_dmeans2D[n * 3] = vis ? ga.x : 0.f;
             p.dL_dmeans2D[n * 3 + 1] = vis ? ga.y : 0.f;
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
             st_count += 1.0f;
             st_radius = max(st_radius, nx_radius_cur);
             const float ddepth = gb.z;
-            float3 dcol = {gb.w, gc.x, gc.y};
+            float3 dcol = {gc.x, gc.y, gc.z};
 
             // ---- cov2D / EWA backward (reference backward.cu:145-295)
             const Ewa e = ewa_project(mean, f.focal_x, f.focal_y, f.tan_fovx, f.tan_fovy, cov3D, V);
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
 #define SH_BWD_THREADS 128
 
 template <int DEG>
-__global__ void __launch_bounds__(SH_BWD_THREADS) k_sh_bwd(const BwdParams p, const float* __restrict__ grad)
+__global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p, const float* __restrict__ grad)
 {
     const FwdParams& f = p.f;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,7 +633,8 @@ __global__ void __launch_bounds__(SH_BWD_THREADS) k_sh_bwd(const BwdParams p, co
         Stage t;
         const size_t n = (size_t)s * f.P + gi;
         t.radius = live ? f.radii[n] : 0;
-        t.cr = grad[n * 12 + 7]; t.cg = grad[n * 12 + 8]; t.cb = grad[n * 12 + 9];
+        const float4 c = reinterpret_cast<const float4*>(grad)[n * 3 + 2];   // (dL/dr, dL/dg, dL/db, -): one sector
+        t.cr = c.x; t.cg = c.y; t.cb = c.z;
         t.mask = __float_as_uint(reinterpret_cast<const float*>(f.geo2 + n)[3]);
         return t;
     };

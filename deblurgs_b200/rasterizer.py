@@ -172,6 +172,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                 cov3Ds_precomp, viewmatrix, projmatrix, raster_settings):
         rs = raster_settings
+        ctx.set_materialize_grads(False)   # an unused output (depth) arrives as None, not as a zero-filled image
         means3D_c, sh_c, colors_c = _f32c(means3D), _f32c(sh), _f32c(colors_precomp)
         opac_c, scales_c, rot_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
         view_c = _f32c(viewmatrix).reshape(1, 4, 4)
@@ -224,6 +225,9 @@ class _RasterizeBlurry(torch.autograd.Function):
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 viewmatrix, projmatrix, campos, raster_settings, blur_denominator, stats_holder=None):
         rs = raster_settings
+        # outputs the loss does not use (typically the [F,3,H,W] / [F,1,H,W] stacks when only `blurred` is) arrive
+        # as None in backward instead of zero-filled tensors the kernel would then have to read
+        ctx.set_materialize_grads(False)
         ctx.stats_holder = stats_holder
         means3D_c, sh_c, colors_c = _f32c(means3D), _f32c(sh), _f32c(colors_precomp)
         opac_c, scales_c, rot_c, cov_c = _f32c(opacities), _f32c(scales), _f32c(rotations), _f32c(cov3Ds_precomp)
