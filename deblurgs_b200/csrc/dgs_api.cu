@@ -85,12 +85,13 @@ static int ref_tile_bits(uint32_t tiles)
 GeomLayout geom_layout(size_t N)
 {
     GeomLayout L;
+    L.n_entries = N;
     size_t o = 0;
     L.geo0 = o; o = align_up(o + N * sizeof(float4));
     L.geo1 = o; o = align_up(o + N * sizeof(float4));
     L.geo2 = o; o = align_up(o + N * sizeof(float4));
     L.tiles = o; o = align_up(o + N * sizeof(uint32_t));
-    L.offsets = o; o = align_up(o + N * sizeof(uint32_t));
+    L.offsets = o; o = align_up(o + (N + 1) * sizeof(uint32_t));   // [N] scan + 1 word: the key-overflow flag
     size_t tmp = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)N);
     tmp += 1024;   // the permuted-input scan may ask for a little more than the plain one
@@ -183,6 +184,7 @@ static void bind_geom(FwdParams& p, char* geom, const GeomLayout& G)
     p.dkeys = (uint64_t*)(geom + G.dkeys);
     p.order_in = (uint32_t*)(geom + G.order_in);
     p.order = (uint32_t*)(geom + G.order);
+    p.key_overflow = p.offsets + G.n_entries;
 }
 
 // tiles[order[i]]: input of the scan over the depth-sorted entry order
@@ -259,29 +261,47 @@ int dgs_blur_forward(
 
     int64_t D = 0;
     if (N > 0) {
+        // Depth sort on a 32-bit key [sub-frame | depth code] (4 radix passes over 8-B pairs) whenever the sub-frame
+        // id leaves >= 27 bits for the depth code; a scene with a visible depth beyond the code's range (reported by
+        // preprocess through key_overflow, read in the one host synchronisation below) is re-sorted on the 64-bit key
+        // [sub-frame | depth bits] (5 passes over 12-B pairs at F = 16), which is also the path for F > 32.
+        p.depth_key_bits = sf_bits <= 5 ? (sf_bits >= 1 ? 32 - sf_bits : 31) : 0;
+        DGS_CUDA(cudaMemsetAsync(p.key_overflow, 0, sizeof(uint32_t), st), "flag memset");
         { StageTimer t(ST_PREPROCESS_FWD, st, 1); launch_preprocess_fwd(p, sh_degree, st); }
-        {
-            // stage 1 of the binning: depth order of the (sub-frame, Gaussian) entries
-            StageTimer t(ST_SORT, st, 0);
-            size_t tmp1 = G.sort_temp_bytes;
-            DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, p.dkeys,
-                                                     (uint64_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
-                                                     (int64_t)N, 0, 32 + sf_bits, st),
-                     "depth sort");
+        uint32_t host_vals[2] = {0u, 0u};   // total duplicates, overflow flag
+        for (int attempt = 0; attempt < 2; attempt++) {
+            {
+                // stage 1 of the binning: depth order of the (sub-frame, Gaussian) entries
+                StageTimer t(ST_SORT, st, 0);
+                size_t tmp1 = G.sort_temp_bytes;
+                if (p.depth_key_bits != 0)
+                    DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, (const uint32_t*)p.dkeys,
+                                                             (uint32_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
+                                                             (int64_t)N, 0, 32, st),
+                             "depth sort (32-bit keys)");
+                else
+                    DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, p.dkeys,
+                                                             (uint64_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
+                                                             (int64_t)N, 0, 32 + sf_bits, st),
+                             "depth sort");
+            }
+            size_t tmp = G.scan_temp_bytes;
+            {
+                StageTimer t(ST_SCAN, st, 0);
+                auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0u),
+                                                          PermutedTiles{p.tiles, p.order});
+                DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, in, p.offsets, (int64_t)N, st), "scan");
+            }
+            // The one host synchronisation of the batched forward (the reference does one per
+            // sub-frame, rasterizer_impl.cu:287): the binning buffer is sized from it.
+            // (offsets[N-1] and the flag word are adjacent: one copy)
+            DGS_CUDA(cudaMemcpyAsync(host_vals, p.offsets + N - 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "num_rendered copy");
+            DGS_CUDA(cudaStreamSynchronize(st), "num_rendered sync");
+            if (p.depth_key_bits == 0 || host_vals[1] == 0u) break;
+            p.depth_key_bits = 0;             // rare: a depth beyond the compact code -> exact 64-bit keys, sort again
+            launch_rebuild_depth_keys(p, st);
         }
-        size_t tmp = G.scan_temp_bytes;
-        {
-            StageTimer t(ST_SCAN, st, 0);
-            auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0u),
-                                                      PermutedTiles{p.tiles, p.order});
-            DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, in, p.offsets, (int64_t)N, st), "scan");
-        }
-        uint32_t total = 0;
-        // The one host synchronisation of the batched forward (the reference does one per
-        // sub-frame, rasterizer_impl.cu:287): the binning buffer is sized from it.
-        DGS_CUDA(cudaMemcpyAsync(&total, p.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "num_rendered copy");
-        DGS_CUDA(cudaStreamSynchronize(st), "num_rendered sync");
-        D = (int64_t)total;
+        D = (int64_t)host_vals[0];
     }
     if (num_rendered) *num_rendered = D;
 

@@ -39,8 +39,10 @@ def test_native_library_is_the_thing_running():
     assert lib.dgs_launch_count(0) - before >= 5
 
 
-def _compare_forward(name, sh_degree=3, use_sigmoid=False, P=None, F=None):
+def _compare_forward(name, sh_degree=3, use_sigmoid=False, P=None, F=None, mutate=None):
     cam, scene, traj, bg, view, proj, campos = pu.make_inputs(name, sh_degree=3, P=P, F=F)
+    if mutate is not None:
+        mutate(scene, view, campos)
     P, F, W, H = scene.means3D.shape[0], view.shape[0], cam.width, cam.height
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     fw = pu.ours_forward(cam, scene, bg, view, proj, campos, sh_degree=sh_degree, use_sigmoid=use_sigmoid)
@@ -84,6 +86,25 @@ def _compare_forward(name, sh_degree=3, use_sigmoid=False, P=None, F=None):
                                           ("tiny", 3, True), ("small", 3, False), ("c1", 3, False)])
 def test_forward_bit_exact_vs_reference_cuda(name, deg, sig):
     _compare_forward(name, sh_degree=deg, use_sigmoid=sig)
+
+
+@needs_ref
+@pytest.mark.parametrize("F,far", [(16, 2.0e9), (32, 5.0e4), (16, 1.0e3), (40, 30.0)])
+def test_depth_key_paths_give_the_reference_order(F, far):
+    """The depth sort uses a 32-bit key [sub-frame | bits(depth) - bits(0.2f)] when F <= 32 (28 / 27 bits of depth code
+    at F = 16 / 32: depths up to 8.6e8 / 1.3e4) and falls back to the exact 64-bit key when a visible depth does not
+    fit, or when F > 32.  Gaussians planted far down the optical axis (2e9 at F=16, 5e4 at F=32) force the fallback;
+    1e3 at F=16 stays on the compact path; F=40 takes the 64-bit path directly.  Lists must be the reference's."""
+    def plant(scene, view, campos):
+        fwd = view[0, :3, 2]                                   # world-space viewing direction of sub-frame 0
+        k = 6
+        g = torch.Generator().manual_seed(3)
+        jitter = (torch.rand(k, 1, generator=g).cuda() * 0.5 + 0.75)
+        scene.means3D[:k] = campos[0][None] + fwd[None] * far * jitter
+        scene.scales[:k] = far * 0.01                          # ~7 px footprint at any distance
+        scene.opacities[:k] = 0.8
+    _, scene, _, view, _, _, fw, refs = _compare_forward("tiny", F=F, mutate=plant)
+    assert int((fw["radii"][0][:6] > 0).sum()) >= 1            # the planted Gaussians are actually rendered
 
 
 @needs_ref
