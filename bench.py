@@ -143,6 +143,7 @@ def flat_grad_views(params):
 
 
 def make_step_ours(w, world):
+    from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     gparams = g.parameters()
     cparams = cmm.parameters()
@@ -159,7 +160,7 @@ def make_step_ours(w, world):
         out = cmm.query(0, "all", background=w["bg"])
         if gt_ready is not None:   # ground truth uploaded on a side stream while the view rendered
             torch.cuda.current_stream().wait_event(gt_ready)
-        loss = (out["blurred"] - gt).abs().mean()
+        loss = blur_photometric_loss(out["blurred"], out["subframes"], gt, 0.0)   # = mean |blurred - gt|, fused
         loss.backward()
         if flat is not None:
             import torch.distributed as dist

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) k_blur_loss_fwd(int F, size_t chw, const 
     double a1 = 0.0, a2 = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += (size_t)gridDim.x * blockDim.x) {
         a1 += (double)fabsf(blur[i] - gt[i]);
+        if (sub == nullptr) continue;   // lambda_t_smooth == 0: the [F,3,H,W] stack is not read at all
         float prev = sub[i];
         float acc = 0.f;
         for (int s = 1; s < F; s++) {
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) k_blur_loss_bwd(int F, size_t chw, const 
     const float k2 = F > 1 ? go * lambda_t / ((float)(F - 1) * (float)chw) : 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += (size_t)gridDim.x * blockDim.x) {
         dblur[i] = sgn(blur[i] - gt[i]) * k1;
+        if (dsub == nullptr) continue;   // lambda_t_smooth == 0: no gradient for the sub-frame stack
         float prev = sub[i];
         float sprev = 0.f;                       // sign(sub[s] - sub[s-1])
         for (int s = 0; s < F; s++) {
@@ -90,7 +92,8 @@ int dgs_blur_loss_forward(int F, int64_t chw, const float* subframes, const floa
                           float lambda_t_smooth, float* loss_out, double* scratch, void* stream)
 {
     if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
-    if (!subframes || !blurred || !gt || !loss_out || !scratch) return DGS_ERR_INVALID_ARGUMENT;
+    if (!blurred || !gt || !loss_out || !scratch) return DGS_ERR_INVALID_ARGUMENT;
+    if (!subframes && lambda_t_smooth != 0.0f) return DGS_ERR_INVALID_ARGUMENT;   // NULL stack only with lambda = 0
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return DGS_ERR_CUDA;
     const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
@@ -104,7 +107,9 @@ int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const flo
                            float* dL_dsubframes, void* stream)
 {
     if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
-    if (!subframes || !blurred || !gt || !dL_dblurred || !dL_dsubframes) return DGS_ERR_INVALID_ARGUMENT;
+    if (!blurred || !gt || !dL_dblurred) return DGS_ERR_INVALID_ARGUMENT;
+    if ((!subframes || !dL_dsubframes) && lambda_t_smooth != 0.0f) return DGS_ERR_INVALID_ARGUMENT;
+    if (!subframes) dL_dsubframes = nullptr;
     const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
     dgs::k_blur_loss_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(F, (size_t)chw, subframes, blurred, gt,
                                                                     lambda_t_smooth, grad_out, dL_dblurred,

@@ -219,7 +219,8 @@ int dgs_pose_backward(int F, int curve_order,
  * 80-93):  loss = mean|blurred - gt| + lambda_t_smooth * mean|subframes[1:] - subframes[:-1]|.
  *   subframes [F, chw], blurred [chw], gt [chw] (chw = 3*H*W), loss_out [3] = (loss, l1, smoothness),
  *   scratch [2] doubles.  Backward: grad_out = device pointer to dL/dloss (NULL = 1), writes
- *   dL_dblurred [chw] and dL_dsubframes [F, chw].
+ *   dL_dblurred [chw] and dL_dsubframes [F, chw].  With lambda_t_smooth == 0 `subframes` / `dL_dsubframes`
+ *   may be NULL: the stack is then neither read nor given a gradient.
  */
 int dgs_blur_loss_forward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
                           float lambda_t_smooth, float* loss_out, double* scratch, void* stream);

@@ -514,3 +514,10 @@ def test_fused_photometric_loss_matches_torch():
             assert torch.allclose(gs, gs_ref, rtol=1e-5, atol=1e-9)
         else:
             assert float(gs.abs().max()) == 0.0
+        # lambda_t_smooth == 0: plain L1, the sub-frame stack is not read and gets no gradient (None, not zeros)
+        mine0 = blur_photometric_loss(blur, sub, gt, 0.0)
+        ref0 = (blur - gt).abs().mean()
+        gb0, gs0 = torch.autograd.grad(mine0 * 1.7, [blur, sub], allow_unused=True)
+        assert abs(mine0.item() - ref0.item()) <= 1e-6 * max(1.0, abs(ref0.item()))
+        assert torch.allclose(gb0, torch.autograd.grad(ref0 * 1.7, [blur])[0], rtol=1e-5, atol=1e-9)
+        assert gs0 is None
