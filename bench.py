@@ -142,7 +142,7 @@ def flat_grad_views(params):
     return flat
 
 
-def make_step_ours(w, world):
+def make_step_ours(w, world, lambda_t_smooth=0.0):
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     gparams = g.parameters()
@@ -160,7 +160,8 @@ def make_step_ours(w, world):
         out = cmm.query(0, "all", background=w["bg"])
         if gt_ready is not None:   # ground truth uploaded on a side stream while the view rendered
             torch.cuda.current_stream().wait_event(gt_ready)
-        loss = blur_photometric_loss(out["blurred"], out["subframes"], gt, 0.0)   # = mean |blurred - gt|, fused
+        # mean |blurred - gt| (+ lambda * mean |subframes[1:] - subframes[:-1]| for --loss smooth), fused
+        loss = blur_photometric_loss(out["blurred"], out["subframes"], gt, lambda_t_smooth)
         loss.backward()
         if flat is not None:
             import torch.distributed as dist
@@ -169,7 +170,7 @@ def make_step_ours(w, world):
     return step
 
 
-def make_step_reference(w):
+def make_step_reference(w, lambda_t_smooth=0.0):
     sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     from oracle import pose_torch as pt   # the reference's Python loop, restated (test infrastructure)
@@ -202,6 +203,8 @@ def make_step_reference(w):
         if gt_ready is not None:
             torch.cuda.current_stream().wait_event(gt_ready)
         loss = (blurred - gt).abs().mean()
+        if lambda_t_smooth != 0.0:   # batchwise_smoothness_loss, utils/loss_utils.py:80-93
+            loss = loss + lambda_t_smooth * (subframes[1:] - subframes[:-1]).abs().mean()
         loss.backward()
         return loss
     return step
@@ -298,6 +301,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--loss", default="l1", choices=["l1", "smooth"],
+                    help="l1: mean|blur - gt| (headline); smooth: + 1e-3 * temporal smoothness of the sub-frames "
+                         "(SURVEY 8d's second variant: non-uniform per-sub-frame gradients)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
@@ -310,17 +316,18 @@ def main():
     eff_world = 1 if args.impl == "reference" else world
     w = build_workload(args.config, rank, device)
     F = w["F"]
+    lam = 1e-3 if args.loss == "smooth" else 0.0
 
     if args.impl == "ours":
         from deblurgs_b200 import _lib
         lib = _lib.load()
-        step = make_step_ours(w, eff_world)
+        step = make_step_ours(w, eff_world, lam)
     else:
         lib = None
         if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "diff_gaussian_rasterization")):
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed"}))
             return
-        step = make_step_reference(w)
+        step = make_step_reference(w, lam)
 
     gt_dev = w["gt_host"].to(device)
     for _ in range(args.warmup):
@@ -365,6 +372,7 @@ def main():
     gt_bufs = [torch.empty_like(gt_dev), torch.empty_like(gt_dev)]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    t_prev, step_wall = t0, []
     for k in range(args.steps):
         gt = gt_bufs[k & 1]
         with torch.cuda.stream(copy_stream):
@@ -372,6 +380,9 @@ def main():
             gt_ready = copy_stream.record_event()
         loss = step(gt, gt_ready)
         loss_host = loss.item()
+        t_now = time.perf_counter()
+        step_wall.append((t_now - t_prev) * 1e3)
+        t_prev = t_now
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if eff_world > 1:
@@ -391,12 +402,15 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_subframe": ms_step / F,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians, %dx%d, num_subframes=%d, SH degree 3, se3 Bezier order %d, "
-                               "one blurry view per GPU per step (fwd+bwd, L1 loss), inputs larger than L2"
-                               % (args.config, w["P"], w["W"], w["H"], F, w["order"]),
+                               "one blurry view per GPU per step (fwd+bwd, %s), inputs larger than L2"
+                               % (args.config, w["P"], w["W"], w["H"], F, w["order"],
+                                  "L1 loss" if lam == 0.0 else "L1 + 1e-3 temporal-smoothness loss"),
                    "parallelism": "views-dp%d" % eff_world, "loss_last": loss_host},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["gt_host"].numel() * 4),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4,
+                "ms_per_step_min_median_max": [round(min(step_wall), 3), round(statistics.median(step_wall), 3),
+                                               round(max(step_wall), 3)]},
     }
     if args.impl == "reference":
         out["impl"] = "reference"
@@ -417,11 +431,13 @@ def main():
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
     out["stage_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1] > 0}
     out["workload_stats"] = st
-    dom = max(stage_ms, key=stage_ms.get)
     sm_mhz = clocks["sm_mhz"] or 1965.0
     n_sm = torch.cuda.get_device_properties(device).multi_processor_count
     fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
     flops = {"render_fwd": 14 * st["E"] + 18 * st["K"], "render_bwd": 16 * st["E_b"] + 88 * st["K"]}
+    # dominant kernel among the stages with an algorithmic work figure (under a profiler the tiny latency-bound
+    # stages can show the largest event times)
+    dom = max((k for k in stage_ms if k in flops or k in abytes), key=stage_ms.get)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):

@@ -34,9 +34,17 @@ __global__ void __launch_bounds__(256) k_activate_fwd(int P, int M, const float*
     const size_t row = (size_t)3 * M, total = (size_t)P * row;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = t0; i < total; i += stride) {
-        const size_t g = i / row, r = i - g * row;
-        sh[i] = r < 3 ? dc[g * 3 + r] : rest[g * (row - 3) + (r - 3)];
+    if (total < 0xF0000000ull) {   // 32-bit index arithmetic (a 64-bit divide per element would make this ALU-bound); headroom for i += stride
+        const uint32_t row32 = (uint32_t)row;
+        for (uint32_t i = (uint32_t)t0; i < (uint32_t)total; i += (uint32_t)stride) {
+            const uint32_t g = i / row32, r = i - g * row32;
+            sh[i] = r < 3 ? dc[g * 3 + r] : rest[(size_t)g * (row32 - 3) + (r - 3)];
+        }
+    } else {
+        for (size_t i = t0; i < total; i += stride) {
+            const size_t g = i / row, r = i - g * row;
+            sh[i] = r < 3 ? dc[g * 3 + r] : rest[g * (row - 3) + (r - 3)];
+        }
     }
     for (size_t g = t0; g < (size_t)P; g += stride) {
         const float s0 = scaling[3 * g], s1 = scaling[3 * g + 1], s2 = scaling[3 * g + 2];
@@ -64,10 +72,19 @@ __global__ void __launch_bounds__(256) k_activate_bwd(int P, int M, const float*
     const size_t row = (size_t)3 * M, total = (size_t)P * row;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = t0; i < total; i += stride) {
-        const size_t g = i / row, r = i - g * row;
-        const float v = dsh ? dsh[i] : 0.f;
-        if (r < 3) ddc[g * 3 + r] = v; else drest[g * (row - 3) + (r - 3)] = v;
+    if (total < 0xF0000000ull) {
+        const uint32_t row32 = (uint32_t)row;
+        for (uint32_t i = (uint32_t)t0; i < (uint32_t)total; i += (uint32_t)stride) {
+            const uint32_t g = i / row32, r = i - g * row32;
+            const float v = dsh ? dsh[i] : 0.f;
+            if (r < 3) ddc[g * 3 + r] = v; else drest[(size_t)g * (row32 - 3) + (r - 3)] = v;
+        }
+    } else {
+        for (size_t i = t0; i < total; i += stride) {
+            const size_t g = i / row, r = i - g * row;
+            const float v = dsh ? dsh[i] : 0.f;
+            if (r < 3) ddc[g * 3 + r] = v; else drest[g * (row - 3) + (r - 3)] = v;
+        }
     }
     for (size_t g = t0; g < (size_t)P; g += stride) {
         // exp: d/dx = exp(x) (torch multiplies by the saved result; the lower bound is an additive constant)
