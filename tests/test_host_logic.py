@@ -94,3 +94,28 @@ def test_compat_packages_resolve_to_the_library(monkeypatch):
     assert dgr.GaussianRasterizer is dg.GaussianRasterizer and knn.distCUDA2 is dg.distCUDA2 and gr.render is dg.render
     for name in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C", "gaussian_renderer"):
         sys.modules.pop(name, None)
+
+
+def test_integer_claims_the_binning_kernels_rely_on():
+    """Two exactness arguments made in csrc/dgs_forward.cu, checked exhaustively / on random data in numpy:
+    (1) k_duplicate recovers (row, column) of duplicate j in a w-wide tile rectangle from a float quotient:
+        trunc((j + 0.5f) / w) == j // w even if the quotient is off by a few ulp (it uses __fdividef);
+    (2) the compact depth key bits(depth) - bits(0.2f) is an exact, order-preserving code of every visible depth."""
+    import numpy as np
+    for w in list(range(1, 130)) + [240, 480, 512, 1023]:
+        j = np.arange(0, w * 1024, dtype=np.int64)            # up to 1024 rows: a 16K-pixel-high image
+        q = ((j.astype(np.float32) + np.float32(0.5)) / np.float32(w)).astype(np.float32)
+        for ulps in (-2, 0, 2):   # __fdividef: <= 2 ulp
+            qq = q if ulps == 0 else (q.view(np.int32) + ulps).view(np.float32)
+            assert np.array_equal(qq.astype(np.int64), j // w), (w, ulps)
+    rng = np.random.default_rng(0)
+    near = np.float32(0.2)
+    d = np.concatenate([np.nextafter(near, np.float32(1.0), dtype=np.float32)[None],
+                        np.exp(rng.uniform(np.log(0.2001), np.log(8.0e8), 200000)).astype(np.float32)])
+    d = d[d > near]
+    code = d.view(np.uint32).astype(np.int64) - int(near.view(np.uint32))
+    assert code.min() >= 1 and code.max() < (1 << 28) - 1          # fits the 28-bit field (F <= 16) up to 8.6e8
+    order_v = np.argsort(d, kind="stable")
+    order_c = np.argsort(code, kind="stable")
+    assert np.array_equal(order_v, order_c)
+    assert np.float32(1.3e4).view(np.uint32) - near.view(np.uint32) < (1 << 27) - 1   # 27-bit field (F <= 32)
