@@ -153,3 +153,39 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("test infrastructure", ""), f
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """include/dgs_b200.h must be consumable by a C compiler (the drop-in boundary is a C ABI, not C++): compile a
+    C99 program that includes it, references every declared entry point, links against libdgs_b200.so and calls
+    the device-free ones."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    names = _declared_symbols()
+    refs = "\n".join("    sink += ((fn_t)&%s != (fn_t)0);" % n for n in names)
+    src = tmp_path / "cabi.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "dgs_b200.h"
+typedef void (*fn_t)(void);
+int main(void) {
+    volatile size_t sink = 0;
+%s
+    int tb = 0, sb = 0;
+    if (dgs_key_bits(600, 400, 16, &tb, &sb) != DGS_OK) return 2;
+    printf("%%d %%d %%d %%d %%d\\n", dgs_version(), dgs_compiled_arch(), tb, sb, (int)(sink != 0));
+    return dgs_adam_step(9, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0.9, 0.999, 1e-15, 0.0, NULL) == DGS_ERR_INVALID_ARGUMENT ? 0 : 3;
+}
+''' % refs)
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-l:libdgs_b200.so", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.split() == ["100", "1000", "10", "4", "1"]
