@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import renderer
+from .densify import DensificationMixin
 from .params import FusedAdam, activate_gaussians
 from .pose import (bezier_se3_poses, c2w_to_minicam_tensors, rotmat_to_unitquat, se3_log_map,
                    unitquat_to_rotmat)
@@ -75,10 +76,11 @@ class BezierModel(nn.Module):
         return (coeff[:, :, None] * self._control_points[idx][None]).sum(dim=1)
 
 
-class GaussianParams:
+class GaussianParams(DensificationMixin):
     """Minimal stand-in for the reference's GaussianModel on the hot path: raw parameters plus the
     activations `render` reads (opacity = clamp(.,0,1), scale = exp(.) + lb, rotation = normalize,
-    features = cat(dc, rest))."""
+    features = cat(dc, rest)), the optimizer (`training_setup`) and the densify / prune mechanics
+    (`densify.DensificationMixin`)."""
 
     def __init__(self, xyz, features_dc, features_rest, scaling, rotation, opacity, active_sh_degree,
                  z_near=0.2, z_far=100.0, use_sigmoid=False, scale_lower_bound=0.0, use_isotropic=False):
@@ -139,7 +141,7 @@ class GaussianParams:
         self.max_radii2D = torch.max(self.max_radii2D, st.max_radius.to(self.max_radii2D.dtype))
 
     def training_setup(self, position_lr_init=0.00016, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005,
-                       rotation_lr=0.001, spatial_lr_scale=1.0):
+                       rotation_lr=0.001, spatial_lr_scale=1.0, percent_dense=0.01, optimizer_cls=None):
         """The reference's optimizer (scene/gaussian_model.py:175-190: Adam, eps=1e-15, one parameter per
         named group), stepped by one fused launch (`params.FusedAdam`)."""
         groups = [
@@ -150,7 +152,8 @@ class GaussianParams:
             {"params": [self._scaling], "lr": scaling_lr, "name": "scaling"},
             {"params": [self._rotation], "lr": rotation_lr, "name": "rotation"},
         ]
-        self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        self.percent_dense = percent_dense
+        self.optimizer = (optimizer_cls or FusedAdam)(groups, lr=0.0, eps=1e-15)
         return self.optimizer
 
     def get_activated(self):
