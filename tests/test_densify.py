@@ -145,7 +145,7 @@ def test_densify_and_prune_round_and_opacity_reset():
     assert float(gp.get_opacity.detach().min()) >= 0.005
     # reset_opacity: capped at 0.1, moments of the opacity tensor zeroed, step count kept
     gp.reset_opacity()
-    assert float(gp._opacity.max()) <= 0.1 + 1e-7 and float(gp._opacity.min()) >= 0.005
+    assert float(gp._opacity.detach().max()) <= 0.1 + 1e-7 and float(gp._opacity.detach().min()) >= 0.005
     st = opt.state[gp._opacity]
     assert float(st["exp_avg"].abs().max()) == 0.0 and float(st["exp_avg_sq"].abs().max()) == 0.0 and st["step"] == 7
     assert opt.param_groups[3]["params"][0] is gp._opacity
