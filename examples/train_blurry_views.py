@@ -13,6 +13,7 @@ What the reference's train.py does per iteration (train.py:120-215), with this r
   loss.backward()                                   one batched backward (+ pose kernel backward)
   for pkg in render_pkgs: add_densification_stats   add_densification_stats_blurry(pkg)  (computed in the backward)
   clip_grad_value_; optimizer.step(); zero_grad     optimizer.step(clip_grad_value=...); zero_grad
+  gaussians.densify_and_prune(threshold, extent)    same name (deblurgs_b200/densify.py; optimizer state follows)
 
 The "ground truth" blurry images are rendered from a hidden scene / trajectories; training starts from perturbed
 colours, opacities and trajectories and must bring the photometric loss down.
@@ -50,6 +51,7 @@ def main():
     ap.add_argument("--subframes", type=int, default=8)
     ap.add_argument("--width", type=int, default=200)
     ap.add_argument("--height", type=int, default=136)
+    ap.add_argument("--densify-every", type=int, default=100, help="0: never")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -107,6 +109,10 @@ def main():
             gauss.add_densification_stats_blurry(out["batched"])    # train.py:188-193, from the backward's epilogue
         opt.step(clip_grad_value=1.0)
         opt.zero_grad(set_to_none=True)
+        if args.densify_every and it > 0 and it % args.densify_every == 0 and it < args.iters - 1:
+            n_before = gauss.get_xyz.shape[0]
+            gauss.densify_and_prune(max_grad=2e-4, extent=5.0)       # train.py:195-196
+            print("iter %4d  densify/prune: %d -> %d Gaussians" % (it, n_before, gauss.get_xyz.shape[0]), flush=True)
         if it % max(args.iters // 10, 1) == 0 or it == args.iters - 1:
             log.append((it, float(loss)))
             print("iter %4d  loss %.5f" % log[-1], flush=True)
