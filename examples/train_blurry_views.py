@@ -114,7 +114,7 @@ def main():
             gauss.densify_and_prune(max_grad=2e-4, extent=5.0)       # train.py:195-196
             print("iter %4d  densify/prune: %d -> %d Gaussians" % (it, n_before, gauss.get_xyz.shape[0]), flush=True)
         if it % max(args.iters // 10, 1) == 0 or it == args.iters - 1:
-            log.append((it, float(loss)))
+            log.append((it, float(loss.detach())))
             print("iter %4d  loss %.5f" % log[-1], flush=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
