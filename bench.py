@@ -450,6 +450,10 @@ def main():
                            "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz (SM clock sampled during the "
                                           "timed region); MEASURED_PEAKS.json has no fp32 entry" % (n_sm, sm_mhz),
                            "algorithmic_flops_per_launch": flops[dom], "ms_per_launch": stage_ms[dom]}
+        if traffic:   # why the bound is not HBM: measured DRAM traffic of the same kernel against the copy bandwidth
+            hbm_pk, _ = measured_peaks()
+            out["roofline"]["dram_gbs"] = traffic / (stage_ms[dom] * 1e-3) / 1e9
+            out["roofline"]["dram_frac_of_hbm_peak"] = out["roofline"]["dram_gbs"] / hbm_pk
     else:
         hbm, src = measured_peaks()
         ach = abytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
