@@ -119,3 +119,47 @@ def test_integer_claims_the_binning_kernels_rely_on():
     order_c = np.argsort(code, kind="stable")
     assert np.array_equal(order_v, order_c)
     assert np.float32(1.3e4).view(np.uint32) - near.view(np.uint32) < (1 << 27) - 1   # 27-bit field (F <= 32)
+
+
+def test_reference_python_binds_to_the_library_through_the_compat_shims(tmp_path):
+    """Drop-in at the import level: with compat/ on the path, the REFERENCE's own, unmodified gaussian_renderer and
+    scene.gaussian_model modules (imported from /root/reference where it is mounted; skipped on the GPU box) resolve
+    `diff_gaussian_rasterization` / `simple_knn._C` to this library's classes.  Third-party modules the hot path never
+    calls (plyfile, open3d, roma, ...) are stubbed when missing.  Runs in a subprocess to keep sys.modules clean."""
+    import os
+    import subprocess
+    import sys
+    ref = os.environ.get("DEBLURGS_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "gaussian_renderer")):
+        pytest.skip("reference tree not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "chain.py"
+    script.write_text('''
+import os, sys, types
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = _Stub(self.__name__ + "." + name)
+        sys.modules[m.__name__] = m
+        return m
+for name in ["roma", "open3d", "plyfile", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "imageio", "lpipsPyTorch"]:
+    try:
+        __import__(name)
+    except Exception:
+        sys.modules[name] = _Stub(name)
+sys.path[:0] = [%r, os.path.join(%r, "compat"), %r]
+import gaussian_renderer, deblurgs_b200
+import scene.gaussian_model as gm
+assert os.path.samefile(os.path.dirname(gaussian_renderer.__file__), os.path.join(%r, "gaussian_renderer"))
+assert gaussian_renderer.GaussianRasterizer is deblurgs_b200.GaussianRasterizer
+assert gaussian_renderer.GaussianRasterizationSettings is deblurgs_b200.GaussianRasterizationSettings
+assert gm.distCUDA2 is deblurgs_b200.distCUDA2
+import inspect
+ours = inspect.signature(deblurgs_b200.render).parameters
+theirs = inspect.signature(gaussian_renderer.render).parameters
+assert list(theirs)[:5] == list(ours)[:5] == ["viewpoint_camera", "pc", "bg_color", "scaling_modifier", "override_color"]
+print("ok")
+''' % (ref, root, root, ref))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
