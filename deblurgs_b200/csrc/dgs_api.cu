@@ -1,15 +1,13 @@
 // C-ABI of libdgs_b200.so (see include/dgs_b200.h for the contract and the reference
 // interfaces each entry point replaces).  Host-side orchestration only: buffer carving,
-// the scan / radix-sort library calls and kernel launches, all on the caller's stream.
+// kernel launches, all on the caller's stream (no library kernels: scan and sorts are dgs_binning.cu).
 #include "dgs_b200.h"
 #include "dgs_internal.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,12 +15,12 @@ namespace dgs {
 
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char* what)
+int fail(int code, const char* what)
 {
     g_last_error = what;
     return code;
 }
-static int fail_cuda(cudaError_t e, const char* where)
+int fail_cuda(cudaError_t e, const char* where)
 {
     g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
     return DGS_ERR_CUDA;
@@ -34,37 +32,42 @@ static int fail_cuda(cudaError_t e, const char* where)
     } while (0)
 
 // ---- stage profiling ---------------------------------------------------------------------
+// Process-wide measurement state; every access is under g_prof_mutex (host threads may drive different
+// devices / streams through the library concurrently), the launch counter is atomic.
 struct ProfRec { cudaEvent_t a, b; int stage; };
-static bool g_prof_on = false;
+static std::mutex g_prof_mutex;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static double g_stage_ms[ST_COUNT];
 static long long g_stage_calls[ST_COUNT];
-static long long g_own_launches = 0;
-static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges",
+static std::atomic<long long> g_own_launches{0};
+static const char* kStageNames[ST_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "tile_sort",
                                             "render_fwd", "blur_mean", "bwd_memset", "render_bwd",
                                             "preprocess_bwd", "pose_fwd", "pose_bwd", "activate_fwd",
-                                            "activate_bwd", "adam"};
-static cudaEvent_t get_event()
+                                            "activate_bwd", "adam", "densify"};
+static cudaEvent_t get_event()   // g_prof_mutex held
 {
     if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
 }
-StageTimer::StageTimer(int stage, cudaStream_t st_, int own_kernels) : idx(-1), st(st_)
+StageTimer::StageTimer(int stage, cudaStream_t st_, int own_kernels) : st(st_), on(false)
 {
-    g_own_launches += own_kernels;
-    if (!g_prof_on) return;
+    g_own_launches.fetch_add(own_kernels, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     ProfRec r;
     r.a = get_event(); r.b = get_event(); r.stage = stage;
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
-    idx = (int)g_prof.size() - 1;
+    end_event = r.b;
+    on = true;
 }
 StageTimer::~StageTimer()
 {
-    if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+    if (on) cudaEventRecord(end_event, st);   // the event handle is ours until dgs_profile_read recycles it
 }
 
 static int bits_for(uint32_t n)  // number of bits needed to hold values 0..n-1 (>= 1)
@@ -82,46 +85,57 @@ static int ref_tile_bits(uint32_t tiles)
     return b < 1 ? 1 : b;
 }
 
-GeomLayout geom_layout(size_t N)
+GeomLayout geom_layout(size_t P, size_t F)
 {
     GeomLayout L;
-    L.n_entries = N;
+    const size_t N = P * F;
+    const size_t Pp = (P + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    const size_t Np = Pp * F;
+    const size_t nb = (P + 1023) / 1024;          // blocks of the entry gather / offsets kernels
+    L.stride = Pp;
     size_t o = 0;
+    // read by the backward (depends on P and F only)
     L.geo0 = o; o = align_up(o + N * sizeof(float4));
     L.geo1 = o; o = align_up(o + N * sizeof(float4));
     L.geo2 = o; o = align_up(o + N * sizeof(float4));
-    L.tiles = o; o = align_up(o + N * sizeof(uint32_t));
-    L.offsets = o; o = align_up(o + (N + 1) * sizeof(uint32_t));   // [N] scan + 1 word: the key-overflow flag
-    size_t tmp = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)N);
-    tmp += 1024;   // the permuted-input scan may ask for a little more than the plain one
-    L.scan_temp_bytes = tmp;
-    L.scan_temp = o; o = align_up(o + tmp);
-    L.dkeys = o; o = align_up(o + N * sizeof(uint64_t));
-    L.dkeys_sorted = o; o = align_up(o + N * sizeof(uint64_t));
-    L.order_in = o; o = align_up(o + N * sizeof(uint32_t));
-    L.order = o; o = align_up(o + N * sizeof(uint32_t));
-    size_t tmp2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)N);
-    L.sort_temp_bytes = tmp2;
-    L.sort_temp = o; o = align_up(o + tmp2);
+    // binning state
+    L.status = o; o = align_up(o + sizeof(BinStatus));
+    L.seg_start = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
+    L.seg_len = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
+    L.seg_adj = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
+    L.ticket = o; o = align_up(o + sizeof(uint32_t));
+    L.rect = o; o = align_up(o + N * sizeof(uint2));
+    L.dkeys = o; o = align_up(o + N * sizeof(uint32_t));
+    L.keys_a = o; o = align_up(o + Np * sizeof(uint32_t));
+    L.keys_b = o; o = align_up(o + Np * sizeof(uint32_t));
+    L.vals_a = o; o = align_up(o + Np * sizeof(uint32_t));
+    L.vals_b = o; o = align_up(o + Np * sizeof(uint32_t));
+    L.cnt_sorted = L.keys_a;                      // the depth sort is finished when the scan stage runs
+    L.off = L.keys_b;
+    L.rec = o; o = align_up(o + Np * sizeof(uint2));
+    L.block_sums = o; o = align_up(o + F * nb * sizeof(unsigned long long));
+    L.block_excl = o; o = align_up(o + F * nb * sizeof(uint32_t));
+    L.sort_scratch = o; o = align_up(o + sort_scratch_bytes((uint32_t)(Np / SORT_CHUNK), 8));
     L.total = o + 128;
     return L;
 }
-BinLayout bin_layout(size_t D)
+// capacity: slots of the duplicate arrays (rounded up to the sort's chunk here)
+BinLayout bin_layout(size_t capacity, size_t F, size_t tiles)
 {
     BinLayout L;
+    (void)F;
+    const size_t C = (capacity + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    L.capacity = C;
+    L.passes = sort_pass_plan(bits_for((uint32_t)(tiles > 1 ? tiles : 1)), &L.bits);
+    const size_t chunks = C / SORT_CHUNK;
     size_t o = 0;
-    L.point_list = o; o = align_up(o + D * sizeof(uint32_t));
-    L.keys = o; o = align_up(o + D * sizeof(uint32_t));
-    L.keys_unsorted = o; o = align_up(o + D * sizeof(uint32_t));
-    L.vals_unsorted = o; o = align_up(o + D * sizeof(uint32_t));
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)D);
-    L.sort_temp_bytes = tmp;
-    L.sort_temp = o; o = align_up(o + tmp);
+    L.point_list = o; o = align_up(o + C * sizeof(uint32_t));
+    L.keys_a = o; if (L.passes >= 2) o = align_up(o + C * sizeof(uint32_t));
+    L.vals_a = o; if (L.passes >= 2) o = align_up(o + C * sizeof(uint32_t));
+    L.keys_b = o; if (L.passes >= 3) o = align_up(o + C * sizeof(uint32_t));
+    L.vals_b = o; if (L.passes >= 3) o = align_up(o + C * sizeof(uint32_t));
+    L.chunk_first = o; o = align_up(o + (chunks + 1) * sizeof(uint32_t));
+    L.sort_scratch = o; o = align_up(o + sort_scratch_bytes((uint32_t)chunks, L.bits));
     L.total = o + 128;
     return L;
 }
@@ -179,20 +193,40 @@ static void bind_geom(FwdParams& p, char* geom, const GeomLayout& G)
     p.geo0 = (float4*)(geom + G.geo0);
     p.geo1 = (float4*)(geom + G.geo1);
     p.geo2 = (float4*)(geom + G.geo2);
-    p.tiles = (uint32_t*)(geom + G.tiles);
-    p.offsets = (uint32_t*)(geom + G.offsets);
-    p.dkeys = (uint64_t*)(geom + G.dkeys);
-    p.order_in = (uint32_t*)(geom + G.order_in);
-    p.order = (uint32_t*)(geom + G.order);
-    p.key_overflow = p.offsets + G.n_entries;
+    p.rect = (uint2*)(geom + G.rect);
+    p.dkeys = (uint32_t*)(geom + G.dkeys);
+}
+static BinState bind_bin_state(char* geom, const GeomLayout& G)
+{
+    BinState b;
+    b.stride = (uint32_t)G.stride;
+    b.order = (const uint32_t*)(geom + G.vals_b);
+    b.cnt_sorted = (uint32_t*)(geom + G.cnt_sorted);
+    b.off = (uint32_t*)(geom + G.off);
+    b.rec = (uint2*)(geom + G.rec);
+    b.block_sums = (unsigned long long*)(geom + G.block_sums);
+    b.block_excl = (uint32_t*)(geom + G.block_excl);
+    b.status = (BinStatus*)(geom + G.status);
+    b.seg_start = (uint32_t*)(geom + G.seg_start);
+    b.seg_len = (uint32_t*)(geom + G.seg_len);
+    b.seg_adj = (uint32_t*)(geom + G.seg_adj);
+    return b;
 }
 
-// tiles[order[i]]: input of the scan over the depth-sorted entry order
-struct PermutedTiles {
-    const uint32_t* tiles;
-    const uint32_t* order;
-    __host__ __device__ uint32_t operator()(uint32_t i) const { return tiles[order[i]]; }
+// Pinned host landing zone of the asynchronous status read-back (one per host thread) and its event.
+struct StatusMailbox {
+    BinStatus* host = nullptr;
+    cudaEvent_t ev[64] = {};
+    cudaEvent_t event()   // of the current device (an event belongs to the device it was created on)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+        if (!host && cudaHostAlloc((void**)&host, sizeof(BinStatus), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        return ev[dev];
+    }
 };
+static thread_local StatusMailbox g_mailbox;
 
 }  // namespace dgs
 
@@ -212,6 +246,164 @@ int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bit
     return DGS_OK;
 }
 
+/* Shared implementation of dgs_blur_forward / dgs_blur_forward_hint.
+ *   capacity_hint == 0  exact mode: the host waits for D after the scan stage (one synchronisation, like the
+ *                       reference's rasterizer_impl.cu:287) and sizes the binning buffer from it.
+ *   capacity_hint  > 0  speculative mode: the binning buffer is sized from the hint and every kernel of the view is
+ *                       enqueued without waiting; D and an overflow flag stay on the device.  With num_rendered !=
+ *                       NULL the host then waits for the small status read-back that was enqueued right after the
+ *                       scan stage (the GPU keeps working on the blend meanwhile) and, if the hint was too small,
+ *                       re-runs the tile sort and the blend with the exact size.  With num_rendered == NULL nothing
+ *                       is waited for (CUDA-graph capturable); query dgs_blur_forward_status afterwards. */
+static int blur_forward_impl(
+    dgs_alloc_fn geom_alloc, void* geom_ctx, dgs_alloc_fn binning_alloc, void* binning_ctx,
+    dgs_alloc_fn image_alloc, void* image_ctx,
+    int P, int F, int sh_degree, int sh_coeffs,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far,
+    int prefiltered, int use_sigmoid,
+    float* out_color, float* out_depth, int* radii,
+    float* out_blur, float blur_denominator,
+    int64_t capacity_hint, int64_t* num_rendered, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_params(p, P, F, sh_coeffs, background, width, height, means3D, shs, colors_precomp,
+                         opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+                         projmatrix, campos, tan_fovx, tan_fovy, z_near, z_far, prefiltered, use_sigmoid);
+    if (rc != DGS_OK) return rc;
+    if (!geom_alloc || !binning_alloc || !image_alloc) return fail(DGS_ERR_INVALID_ARGUMENT, "null allocator");
+    if (F > 0 && width * height > 0 && (!out_color || !out_depth)) return fail(DGS_ERR_INVALID_ARGUMENT, "null output");
+    if (shs != nullptr && (sh_degree < 0 || sh_degree > 3 || sh_coeffs < (sh_degree + 1) * (sh_degree + 1)))
+        return fail(DGS_ERR_INVALID_ARGUMENT, "bad SH degree / coefficient count");
+    if (P > 0 && F > 0 && !radii) return fail(DGS_ERR_INVALID_ARGUMENT, "null radii");
+    if (capacity_hint < 0) return fail(DGS_ERR_INVALID_ARGUMENT, "negative binning capacity");
+    p.radii = radii;
+
+    const size_t N = (size_t)P * F;
+    const size_t tiles = (size_t)p.tiles_x * p.tiles_y;
+    const size_t pixels = (size_t)width * height;
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
+    if (G.stride * (size_t)F >= (1ull << 32)) return fail(DGS_ERR_UNSUPPORTED, "P*F must be < 2^32");
+    // the packed tile rectangle of the duplicate generator holds 10 bits per coordinate
+    if (p.tiles_x > 1024 || p.tiles_y > 1024) return fail(DGS_ERR_UNSUPPORTED, "image larger than 16384 pixels per side");
+
+    const ImgLayout I = img_layout(F, tiles, pixels);
+    char* geom = geom_alloc(geom_ctx, G.total);
+    char* img = image_alloc(image_ctx, I.total);
+    if (!geom || !img) return fail(DGS_ERR_ALLOC, "state buffer allocation failed");
+    geom = aligned128(geom);
+    img = aligned128(img);
+    bind_geom(p, geom, G);
+    const BinState bs = bind_bin_state(geom, G);
+    uint2* ranges = (uint2*)(img + I.ranges);
+    float* final_T = (float*)(img + I.final_T);
+    uint32_t* n_contrib = (uint32_t*)(img + I.n_contrib);
+    uint32_t* ticket = (uint32_t*)(geom + G.ticket);
+
+    int64_t D = 0;
+    const size_t pad = (size_t)F * SORT_CHUNK;          // every sub-frame's list is padded to the sort's chunk
+    size_t capacity = capacity_hint > 0 ? (size_t)capacity_hint + pad : 0;
+    cudaEvent_t ev = nullptr;
+    const bool speculative = capacity_hint > 0;
+    if (N > 0) {
+        DGS_CUDA(cudaMemsetAsync(geom + G.status, 0, G.rect - G.status, st), "status memset");   // status .. ticket
+        { StageTimer t(ST_PREPROCESS_FWD, st, 1); launch_preprocess_fwd(p, sh_degree, st); }
+        {
+            // stage 1: depth order of the Gaussians of every sub-frame (segmented sort on the 32 depth bits)
+            StageTimer t(ST_DEPTH_SORT, st, 12);
+            const SortScratch sc = bind_sort_scratch(geom + G.sort_scratch, (uint32_t)(G.stride * F / SORT_CHUNK), 8, ticket);
+            sort_uniform_u32(F, (uint32_t)P, (uint32_t)G.stride, p.dkeys, (uint32_t*)(geom + G.keys_a),
+                             (uint32_t*)(geom + G.vals_a), (uint32_t*)(geom + G.keys_b), (uint32_t*)(geom + G.vals_b),
+                             sc, 32, st);
+        }
+        if (!speculative) {
+            // exact mode: D is needed on the host to size the binning buffer
+            { StageTimer t(ST_SCAN, st, 2); launch_entry_scan(p, bs, ~0ull, st); }
+            BinStatus h;
+            DGS_CUDA(cudaMemcpyAsync(&h, bs.status, sizeof(h), cudaMemcpyDeviceToHost, st), "num_rendered copy");
+            DGS_CUDA(cudaStreamSynchronize(st), "num_rendered sync");
+            if (h.padded + SORT_CHUNK >= (1ull << 32))
+                return fail(DGS_ERR_UNSUPPORTED, "more than 2^32 (Gaussian, tile) duplicates in one batched view");
+            D = (int64_t)h.num_rendered;
+            capacity = (size_t)h.padded;
+            // the status words were computed against an unlimited capacity: overflow = 0, n_chunks = padded / chunk
+        } else {
+            if (capacity + SORT_CHUNK >= (1ull << 32)) capacity = (1ull << 32) - 2 * SORT_CHUNK;
+            { StageTimer t(ST_SCAN, st, 2); launch_entry_scan(p, bs, (unsigned long long)(capacity / SORT_CHUNK * SORT_CHUNK), st); }
+            if (num_rendered) {
+                ev = g_mailbox.event();
+                if (!ev) return fail(DGS_ERR_CUDA, "status mailbox allocation failed");
+                DGS_CUDA(cudaMemcpyAsync(g_mailbox.host, bs.status, sizeof(BinStatus), cudaMemcpyDeviceToHost, st), "status copy");
+                DGS_CUDA(cudaEventRecord(ev, st), "status event");
+            }
+        }
+    }
+
+    char* bin = nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const BinLayout B = bin_layout(capacity, F, tiles);
+        bin = binning_alloc(binning_ctx, B.total);
+        if (!bin) return fail(DGS_ERR_ALLOC, "binning buffer allocation failed");
+        bin = aligned128(bin);
+        uint32_t* point_list = (uint32_t*)(bin + B.point_list);
+        uint32_t* chunk_first = (uint32_t*)(bin + B.chunk_first);
+
+        if (F > 0 && tiles > 0)
+            DGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)F * tiles * sizeof(uint2), st), "ranges memset");
+        if (N > 0 && B.capacity > 0) {
+            { StageTimer t(ST_SCAN, st, 1); launch_entry_offsets(p, bs, chunk_first, st); }
+            // stage 2: duplicates generated from the depth-ordered entries and sorted by tile id inside every
+            // sub-frame's segment; the last pass writes point_list and the per-tile ranges
+            StageTimer t(ST_TILE_SORT, st, 3 * B.passes);
+            SegTable tab;
+            memset(&tab, 0, sizeof(tab));
+            tab.seg_start = bs.seg_start; tab.seg_len = bs.seg_len; tab.seg_adj = bs.seg_adj;
+            tab.n_chunks = &bs.status->n_chunks; tab.nseg = F;
+            GenParams gp;
+            gp.off = bs.off; gp.rec = bs.rec; gp.chunk_first = chunk_first;
+            gp.entries_per_seg = (uint32_t)P; gp.entry_stride = bs.stride; gp.tiles_x = p.tiles_x;
+            const uint32_t max_chunks = (uint32_t)(B.capacity / SORT_CHUNK);
+            const SortScratch sc = bind_sort_scratch(bin + B.sort_scratch, max_chunks, B.bits, ticket);
+            uint32_t* ka = (uint32_t*)(bin + B.keys_a); uint32_t* va = (uint32_t*)(bin + B.vals_a);
+            uint32_t* kb = (uint32_t*)(bin + B.keys_b); uint32_t* vb = (uint32_t*)(bin + B.vals_b);
+            const uint32_t* kin = nullptr; const uint32_t* vin = nullptr;
+            for (int pass = 0; pass < B.passes; pass++) {
+                const bool last = pass == B.passes - 1;
+                uint32_t* ko = last ? nullptr : (pass == 0 ? ka : kb);
+                uint32_t* vo = last ? point_list : (pass == 0 ? va : vb);
+                sort_pass(tab, max_chunks, B.bits, B.bits * pass, kin, vin, 0, ko, vo, sc, pass == 0 ? &gp : nullptr,
+                          last ? ranges : nullptr, (uint32_t)tiles, st);
+                kin = ko; vin = vo;
+            }
+        }
+        if (F > 0 && pixels > 0) {
+            { StageTimer t(ST_RENDER_FWD, st, 1); launch_render_fwd(p, ranges, point_list, final_T, n_contrib, out_color, out_depth, st); }
+            if (out_blur) { StageTimer t(ST_BLUR_MEAN, st, 1); launch_blur_mean(out_color, F, 3 * pixels, blur_denominator, out_blur, st); }
+        }
+        DGS_CUDA(cudaGetLastError(), "forward launch");
+        if (!ev) break;
+        // speculative mode with a host-visible result: the status was copied right after the scan stage
+        DGS_CUDA(cudaEventSynchronize(ev), "status wait");
+        const BinStatus h = *g_mailbox.host;
+        ev = nullptr;
+        D = (int64_t)h.num_rendered;
+        if (!h.overflow) break;
+        if (h.padded + SORT_CHUNK >= (1ull << 32))
+            return fail(DGS_ERR_UNSUPPORTED, "more than 2^32 (Gaussian, tile) duplicates in one batched view");
+        // the hint was too small: the tile sort did nothing.  Redo the scan stage against the exact size.
+        capacity = (size_t)h.padded;
+        { StageTimer t(ST_SCAN, st, 2); launch_entry_scan(p, bs, ~0ull, st); }
+    }
+    if (num_rendered) *num_rendered = D;
+    return DGS_OK;
+}
+
 int dgs_blur_forward(
     dgs_alloc_fn geom_alloc, void* geom_ctx, dgs_alloc_fn binning_alloc, void* binning_ctx,
     dgs_alloc_fn image_alloc, void* image_ctx,
@@ -227,112 +419,48 @@ int dgs_blur_forward(
     float* out_blur, float blur_denominator,
     int64_t* num_rendered, void* stream)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    FwdParams p;
-    memset(&p, 0, sizeof(p));
-    int rc = fill_params(p, P, F, sh_coeffs, background, width, height, means3D, shs, colors_precomp,
-                         opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
-                         projmatrix, campos, tan_fovx, tan_fovy, z_near, z_far, prefiltered, use_sigmoid);
-    if (rc != DGS_OK) return rc;
-    if (!geom_alloc || !binning_alloc || !image_alloc) return fail(DGS_ERR_INVALID_ARGUMENT, "null allocator");
-    if (F > 0 && width * height > 0 && (!out_color || !out_depth)) return fail(DGS_ERR_INVALID_ARGUMENT, "null output");
-    if (shs != nullptr && (sh_degree < 0 || sh_degree > 3 || sh_coeffs < (sh_degree + 1) * (sh_degree + 1)))
-        return fail(DGS_ERR_INVALID_ARGUMENT, "bad SH degree / coefficient count");
-    if (P > 0 && F > 0 && !radii) return fail(DGS_ERR_INVALID_ARGUMENT, "null radii");
-    p.radii = radii;
+    return blur_forward_impl(geom_alloc, geom_ctx, binning_alloc, binning_ctx, image_alloc, image_ctx, P, F, sh_degree,
+                             sh_coeffs, background, width, height, means3D, shs, colors_precomp, opacities, scales,
+                             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
+                             tan_fovy, z_near, z_far, prefiltered, use_sigmoid, out_color, out_depth, radii, out_blur,
+                             blur_denominator, 0, num_rendered, stream);
+}
 
-    const size_t N = (size_t)P * F;
-    const size_t tiles = (size_t)p.tiles_x * p.tiles_y;
-    const size_t pixels = (size_t)width * height;
-    const int sf_bits = F > 1 ? bits_for((uint32_t)F) : 0;
-    if (N >= (1ull << 32)) return fail(DGS_ERR_UNSUPPORTED, "P*F must be < 2^32");
+int dgs_blur_forward_hint(
+    dgs_alloc_fn geom_alloc, void* geom_ctx, dgs_alloc_fn binning_alloc, void* binning_ctx,
+    dgs_alloc_fn image_alloc, void* image_ctx,
+    int P, int F, int sh_degree, int sh_coeffs,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far,
+    int prefiltered, int use_sigmoid,
+    float* out_color, float* out_depth, int* radii,
+    float* out_blur, float blur_denominator,
+    int64_t binning_capacity, int64_t* num_rendered, void* stream)
+{
+    return blur_forward_impl(geom_alloc, geom_ctx, binning_alloc, binning_ctx, image_alloc, image_ctx, P, F, sh_degree,
+                             sh_coeffs, background, width, height, means3D, shs, colors_precomp, opacities, scales,
+                             scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
+                             tan_fovy, z_near, z_far, prefiltered, use_sigmoid, out_color, out_depth, radii, out_blur,
+                             blur_denominator, binning_capacity, num_rendered, stream);
+}
 
-    const GeomLayout G = geom_layout(N);
-    const ImgLayout I = img_layout(F, tiles, pixels);
-    char* geom = geom_alloc(geom_ctx, G.total);
-    char* img = image_alloc(image_ctx, I.total);
-    if (!geom || !img) return fail(DGS_ERR_ALLOC, "state buffer allocation failed");
-    geom = aligned128(geom);
-    img = aligned128(img);
-    bind_geom(p, geom, G);
-    uint2* ranges = (uint2*)(img + I.ranges);
-    float* final_T = (float*)(img + I.final_T);
-    uint32_t* n_contrib = (uint32_t*)(img + I.n_contrib);
-
-    int64_t D = 0;
-    if (N > 0) {
-        // Depth sort on a 32-bit key [sub-frame | depth code] (4 radix passes over 8-B pairs) whenever the sub-frame
-        // id leaves >= 27 bits for the depth code; a scene with a visible depth beyond the code's range (reported by
-        // preprocess through key_overflow, read in the one host synchronisation below) is re-sorted on the 64-bit key
-        // [sub-frame | depth bits] (5 passes over 12-B pairs at F = 16), which is also the path for F > 32.
-        p.depth_key_bits = sf_bits <= 5 ? (sf_bits >= 1 ? 32 - sf_bits : 31) : 0;
-        DGS_CUDA(cudaMemsetAsync(p.key_overflow, 0, sizeof(uint32_t), st), "flag memset");
-        { StageTimer t(ST_PREPROCESS_FWD, st, 1); launch_preprocess_fwd(p, sh_degree, st); }
-        uint32_t host_vals[2] = {0u, 0u};   // total duplicates, overflow flag
-        for (int attempt = 0; attempt < 2; attempt++) {
-            {
-                // stage 1 of the binning: depth order of the (sub-frame, Gaussian) entries
-                StageTimer t(ST_SORT, st, 0);
-                size_t tmp1 = G.sort_temp_bytes;
-                if (p.depth_key_bits != 0)
-                    DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, (const uint32_t*)p.dkeys,
-                                                             (uint32_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
-                                                             (int64_t)N, 0, 32, st),
-                             "depth sort (32-bit keys)");
-                else
-                    DGS_CUDA(cub::DeviceRadixSort::SortPairs(geom + G.sort_temp, tmp1, p.dkeys,
-                                                             (uint64_t*)(geom + G.dkeys_sorted), p.order_in, p.order,
-                                                             (int64_t)N, 0, 32 + sf_bits, st),
-                             "depth sort");
-            }
-            size_t tmp = G.scan_temp_bytes;
-            {
-                StageTimer t(ST_SCAN, st, 0);
-                auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint32_t>(0u),
-                                                          PermutedTiles{p.tiles, p.order});
-                DGS_CUDA(cub::DeviceScan::InclusiveSum(geom + G.scan_temp, tmp, in, p.offsets, (int64_t)N, st), "scan");
-            }
-            // The one host synchronisation of the batched forward (the reference does one per
-            // sub-frame, rasterizer_impl.cu:287): the binning buffer is sized from it.
-            // (offsets[N-1] and the flag word are adjacent: one copy)
-            DGS_CUDA(cudaMemcpyAsync(host_vals, p.offsets + N - 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "num_rendered copy");
-            DGS_CUDA(cudaStreamSynchronize(st), "num_rendered sync");
-            if (p.depth_key_bits == 0 || host_vals[1] == 0u) break;
-            p.depth_key_bits = 0;             // rare: a depth beyond the compact code -> exact 64-bit keys, sort again
-            launch_rebuild_depth_keys(p, st);
-        }
-        D = (int64_t)host_vals[0];
-    }
-    if (num_rendered) *num_rendered = D;
-
-    const BinLayout B = bin_layout((size_t)D);
-    char* bin = binning_alloc(binning_ctx, B.total);
-    if (!bin) return fail(DGS_ERR_ALLOC, "binning buffer allocation failed");
-    bin = aligned128(bin);
-    uint32_t* point_list = (uint32_t*)(bin + B.point_list);
-    uint32_t* keys = (uint32_t*)(bin + B.keys);
-    uint32_t* keys_unsorted = (uint32_t*)(bin + B.keys_unsorted);
-    uint32_t* vals_unsorted = (uint32_t*)(bin + B.vals_unsorted);
-
-    if (F > 0 && tiles > 0)
-        DGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)F * tiles * sizeof(uint2), st), "ranges memset");
-    if (D > 0) {
-        { StageTimer t(ST_DUPLICATE, st, 1); launch_duplicate(p, keys_unsorted, vals_unsorted, st); }
-        size_t tmp = B.sort_temp_bytes;
-        {
-            // stage 2: stable sort of the duplicates on the short [sub-frame | tile] key
-            StageTimer t(ST_SORT, st, 0);
-            DGS_CUDA(cub::DeviceRadixSort::SortPairs(bin + B.sort_temp, tmp, keys_unsorted, keys, vals_unsorted,
-                                                     point_list, (int64_t)D, 0, p.tile_bits + sf_bits, st),
-                     "tile sort");
-        }
-        { StageTimer t(ST_TILE_RANGES, st, 1); launch_tile_ranges(D, keys, p.tile_bits, (int)tiles, ranges, st); }
-    }
-    if (F > 0 && pixels > 0) {
-        { StageTimer t(ST_RENDER_FWD, st, 1); launch_render_fwd(p, ranges, point_list, final_T, n_contrib, out_color, out_depth, st); }
-        if (out_blur) { StageTimer t(ST_BLUR_MEAN, st, 1); launch_blur_mean(out_color, F, 3 * pixels, blur_denominator, out_blur, st); }
-    }
-    DGS_CUDA(cudaGetLastError(), "forward launch");
+int dgs_blur_forward_status(const char* geom_buffer, int P, int F, int64_t* num_rendered, int* overflow, void* stream)
+{
+    if (num_rendered) *num_rendered = 0;
+    if (overflow) *overflow = 0;
+    if ((size_t)P * (size_t)F == 0) return DGS_OK;
+    if (!geom_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null geometry buffer");
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
+    BinStatus h;
+    DGS_CUDA(cudaMemcpyAsync(&h, aligned128((char*)geom_buffer) + G.status, sizeof(h), cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream), "status copy");
+    DGS_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "status sync");
+    if (num_rendered) *num_rendered = (int64_t)h.num_rendered;
+    if (overflow) *overflow = (int)h.overflow;
     return DGS_OK;
 }
 
@@ -381,9 +509,8 @@ int dgs_blur_backward(
     const size_t N = (size_t)P * F;
     const size_t tiles = (size_t)b.f.tiles_x * b.f.tiles_y;
     const size_t pixels = (size_t)width * height;
-    const GeomLayout G = geom_layout(N);
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
     const ImgLayout I = img_layout(F, tiles, pixels);
-    const BinLayout B = bin_layout((size_t)num_rendered);
     char* geom = aligned128((char*)geom_buffer);
     char* img = aligned128((char*)image_buffer);
     char* bin = aligned128((char*)binning_buffer);
@@ -392,7 +519,7 @@ int dgs_blur_backward(
     b.ranges = (const uint2*)(img + I.ranges);
     b.final_T = (const float*)(img + I.final_T);
     b.n_contrib = (const uint32_t*)(img + I.n_contrib);
-    b.point_list = (const uint32_t*)(bin + B.point_list);
+    b.point_list = (const uint32_t*)bin;   // point_list is the first array of the binning buffer
     b.dL_dpix = dL_dpix;
     b.dL_dpixdepth = dL_dpixdepth;
     b.dL_dblur = dL_dblur;
@@ -410,7 +537,8 @@ int dgs_blur_backward(
         StageTimer t(ST_BWD_MEMSET, st, 0);
         DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
     }
-    if (num_rendered > 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
+    // num_rendered is informational (the lists are delimited by the per-tile ranges); < 0 = unknown (speculative forward)
+    if (num_rendered != 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
     { StageTimer t(ST_PREPROCESS_BWD, st, colors_precomp ? 2 : 3); launch_preprocess_bwd(b, sh_degree, st); }
     DGS_CUDA(cudaGetLastError(), "backward launch");
     return DGS_OK;
@@ -464,13 +592,14 @@ int dgs_backward(
 // ---- profiling / measurement ------------------------------------------------------------
 int dgs_profile_enable(int on)
 {
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
     return DGS_OK;
 }
 int dgs_profile_num_stages(void) { return ST_COUNT; }
 const char* dgs_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 int dgs_profile_read(double* ms, int64_t* calls, int n, int reset)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& r : g_prof) {
         float t = 0.f;
         cudaError_t e = cudaEventSynchronize(r.b);
@@ -493,21 +622,7 @@ int dgs_profile_read(double* ms, int64_t* calls, int n, int reset)
 }
 int64_t dgs_launch_count(int reset)
 {
-    const int64_t v = g_own_launches;
-    if (reset) g_own_launches = 0;
-    return v;
-}
-void dgs_profile_note(int stage, void* stream, int own_kernels, int begin, int* token)
-{
-    // used by translation units that cannot see StageTimer's storage (pose kernels)
-    if (begin) {
-        StageTimer* t = new StageTimer(stage, (cudaStream_t)stream, own_kernels);
-        *token = t->idx;
-        t->idx = -1;   // do not record the end event on destruction
-        delete t;
-    } else if (*token >= 0 && *token < (int)g_prof.size()) {
-        cudaEventRecord(g_prof[*token].b, (cudaStream_t)stream);
-    }
+    return reset ? g_own_launches.exchange(0) : g_own_launches.load();
 }
 
 int dgs_debug_workload(const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
@@ -522,30 +637,32 @@ int dgs_debug_workload(const char* geom_buffer, const char* binning_buffer, cons
     p.P = P; p.F = F; p.W = width; p.H = height;
     p.tiles_x = (width + DGS_TILE_X - 1) / DGS_TILE_X;
     p.tiles_y = (height + DGS_TILE_Y - 1) / DGS_TILE_Y;
-    const size_t N = (size_t)P * F, tiles = (size_t)p.tiles_x * p.tiles_y, pixels = (size_t)width * height;
-    const GeomLayout G = geom_layout(N);
+    const size_t tiles = (size_t)p.tiles_x * p.tiles_y, pixels = (size_t)width * height;
+    (void)num_rendered;
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
     const ImgLayout I = img_layout(F, tiles, pixels);
-    const BinLayout B = bin_layout((size_t)num_rendered);
     char* geom = aligned128((char*)geom_buffer);
     char* img = aligned128((char*)image_buffer);
     char* bin = aligned128((char*)binning_buffer);
     bind_geom(p, geom, G);
     DGS_CUDA(cudaMemsetAsync(out_dev, 0, 3 * sizeof(uint64_t), st), "workload memset");
-    launch_workload(p, (const uint2*)(img + I.ranges), (const uint32_t*)(bin + B.point_list),
+    launch_workload(p, (const uint2*)(img + I.ranges), (const uint32_t*)bin,
                     (const uint32_t*)(img + I.n_contrib), (unsigned long long*)out_dev, st);
     DGS_CUDA(cudaGetLastError(), "workload");
     return DGS_OK;
 }
 
 // ---- debug / parity accessors ---------------------------------------------------------
-__global__ void k_debug_geometry(size_t N, const float4* g0, const float4* g1, const float4* g2,
-                                 const uint32_t* tiles, const uint32_t* offsets, float* depths,
+__global__ void k_debug_geometry(int P, int F, uint32_t stride, const float4* g0, const float4* g1, const float4* g2,
+                                 const uint2* rect, const uint32_t* off, float* depths,
                                  float* means2D, float* conic_opacity, float* rgb, float* clamped,
                                  uint32_t* tiles_out, uint32_t* offsets_out)
 {
     const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const bool vis = tiles[n] > 0;
+    if (n >= (size_t)P * F) return;
+    const uint2 r = rect[n];
+    const uint32_t cnt = (r.y & 0xFFFFu) * (r.y >> 16);
+    const bool vis = cnt > 0;
     float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
     if (vis) { a = g0[n]; b = g1[n]; c = g2[n]; }
     if (depths) depths[n] = a.z;
@@ -556,8 +673,8 @@ __global__ void k_debug_geometry(size_t N, const float4* g0, const float4* g1, c
         const unsigned m = vis ? __float_as_uint(c.w) : 0u;
         clamped[3 * n] = (m & 1u) ? 1.f : 0.f; clamped[3 * n + 1] = (m & 2u) ? 1.f : 0.f; clamped[3 * n + 2] = (m & 4u) ? 1.f : 0.f;
     }
-    if (tiles_out) tiles_out[n] = tiles[n];
-    if (offsets_out) offsets_out[n] = offsets[n];
+    if (tiles_out) tiles_out[n] = cnt;
+    if (offsets_out) { const size_t s = n / P, i = n - s * P; offsets_out[n] = off[s * stride + i]; }
 }
 
 int dgs_debug_geometry(const char* geom_buffer, int P, int F, float* depths, float* means2D,
@@ -567,42 +684,39 @@ int dgs_debug_geometry(const char* geom_buffer, int P, int F, float* depths, flo
     const size_t N = (size_t)P * F;
     if (N == 0) return DGS_OK;
     if (!geom_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null geometry buffer");
-    const GeomLayout G = geom_layout(N);
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
     char* geom = aligned128((char*)geom_buffer);
     k_debug_geometry<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        N, (const float4*)(geom + G.geo0), (const float4*)(geom + G.geo1), (const float4*)(geom + G.geo2),
-        (const uint32_t*)(geom + G.tiles), (const uint32_t*)(geom + G.offsets), depths, means2D,
-        conic_opacity, rgb, clamped, tiles_touched, point_offsets);
+        P, F, (uint32_t)G.stride, (const float4*)(geom + G.geo0), (const float4*)(geom + G.geo1),
+        (const float4*)(geom + G.geo2), (const uint2*)(geom + G.rect), (const uint32_t*)(geom + G.off), depths,
+        means2D, conic_opacity, rgb, clamped, tiles_touched, point_offsets);
     DGS_CUDA(cudaGetLastError(), "debug geometry");
     return DGS_OK;
 }
 
-int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, int P, int F, int width, int height,
-                      int64_t num_rendered, uint64_t* keys, uint32_t* point_list, void* stream)
+int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, const char* image_buffer, int P, int F,
+                      int width, int height, int64_t num_rendered, uint64_t* keys, uint32_t* point_list,
+                      uint32_t* ranges, void* stream)
 {
-    if (num_rendered <= 0) return DGS_OK;
-    if (!binning_buffer || !geom_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null state buffer");
-    const BinLayout B = bin_layout((size_t)num_rendered);
+    if (F <= 0 || P <= 0) return DGS_OK;
+    if (!binning_buffer || !geom_buffer || !image_buffer) return fail(DGS_ERR_INVALID_ARGUMENT, "null state buffer");
+    (void)num_rendered;
+    const int tx = (width + DGS_TILE_X - 1) / DGS_TILE_X, ty = (height + DGS_TILE_Y - 1) / DGS_TILE_Y;
+    const size_t tiles = (size_t)tx * ty, pixels = (size_t)width * height;
+    const GeomLayout G = geom_layout((size_t)P, (size_t)F);
+    const ImgLayout I = img_layout(F, tiles, pixels);
+    char* geom = aligned128((char*)geom_buffer);
+    char* img = aligned128((char*)image_buffer);
     char* bin = aligned128((char*)binning_buffer);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (keys) {
-        FwdParams p;
-        memset(&p, 0, sizeof(p));
-        p.P = P; p.F = F; p.W = width; p.H = height;
-        p.tiles_x = (width + DGS_TILE_X - 1) / DGS_TILE_X;
-        p.tiles_y = (height + DGS_TILE_Y - 1) / DGS_TILE_Y;
-        p.tile_bits = ref_tile_bits((uint32_t)(p.tiles_x * p.tiles_y));
-        bind_geom(p, aligned128((char*)geom_buffer), geom_layout((size_t)P * F));
-        launch_rebuild_keys(p, num_rendered, (const uint32_t*)(bin + B.keys), (const uint32_t*)(bin + B.point_list),
-                            keys, st);
-        DGS_CUDA(cudaGetLastError(), "rebuild keys");
-    }
-    if (point_list) DGS_CUDA(cudaMemcpyAsync(point_list, bin + B.point_list, num_rendered * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy list");
+    launch_debug_lists(P, F, (int)tiles, ref_tile_bits((uint32_t)tiles), (const uint2*)(img + I.ranges),
+                       (const uint32_t*)bin, (const float4*)(geom + G.geo0), (const uint32_t*)(geom + G.seg_start),
+                       (const uint32_t*)(geom + G.seg_adj), keys, point_list, ranges, (cudaStream_t)stream);
+    DGS_CUDA(cudaGetLastError(), "debug lists");
     return DGS_OK;
 }
 
-int dgs_debug_image(const char* image_buffer, int F, int width, int height, uint32_t* ranges,
-                    float* final_T, uint32_t* n_contrib, void* stream)
+int dgs_debug_image(const char* image_buffer, int F, int width, int height, float* final_T, uint32_t* n_contrib,
+                    void* stream)
 {
     const size_t tiles = (size_t)((width + DGS_TILE_X - 1) / DGS_TILE_X) * ((height + DGS_TILE_Y - 1) / DGS_TILE_Y);
     const size_t pixels = (size_t)width * height;
@@ -611,9 +725,50 @@ int dgs_debug_image(const char* image_buffer, int F, int width, int height, uint
     const ImgLayout I = img_layout(F, tiles, pixels);
     char* img = aligned128((char*)image_buffer);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ranges && tiles) DGS_CUDA(cudaMemcpyAsync(ranges, img + I.ranges, F * tiles * sizeof(uint2), cudaMemcpyDeviceToDevice, st), "copy ranges");
     if (final_T && pixels) DGS_CUDA(cudaMemcpyAsync(final_T, img + I.final_T, F * pixels * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy T");
     if (n_contrib && pixels) DGS_CUDA(cudaMemcpyAsync(n_contrib, img + I.n_contrib, F * pixels * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), "copy n_contrib");
+    return DGS_OK;
+}
+
+/* Debug entry of the segmented radix sort (dgs_binning.cu): sorts keys [nseg][len] (device, u32) on their low
+ * key_bits bits, segment by segment, stable; writes the sorted keys and the source index inside the segment.
+ * scratch: dgs_debug_sort_scratch_bytes(nseg, len). */
+size_t dgs_debug_sort_scratch_bytes(int nseg, int64_t len)
+{
+    const size_t stride = ((size_t)len + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    const size_t Np = stride * (size_t)(nseg > 0 ? nseg : 0);
+    return 4 * align_up(Np * 4) + sort_scratch_bytes((uint32_t)(Np / SORT_CHUNK), 8) + 512;
+}
+__global__ void k_debug_unpad(int nseg, uint32_t len, uint32_t stride, const uint32_t* a, const uint32_t* b,
+                              uint32_t* out_a, uint32_t* out_b)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nseg * len) return;
+    const size_t s = i / len, j = i - s * len;
+    if (out_a) out_a[i] = a[s * stride + j];
+    if (out_b) out_b[i] = b[s * stride + j];
+}
+int dgs_debug_sort(int nseg, int64_t len, int key_bits, const uint32_t* keys, uint32_t* keys_sorted,
+                   uint32_t* index_sorted, char* scratch, void* stream)
+{
+    if (nseg <= 0 || len <= 0) return DGS_OK;
+    if (!keys || !scratch || key_bits < 1 || key_bits > 32) return fail(DGS_ERR_INVALID_ARGUMENT, "dgs_debug_sort: invalid argument");
+    const size_t stride = ((size_t)len + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    const size_t Np = stride * (size_t)nseg;
+    if (Np >= (1ull << 32)) return fail(DGS_ERR_UNSUPPORTED, "dgs_debug_sort: too many items");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* sc = aligned128(scratch);
+    uint32_t* ka = (uint32_t*)sc; sc += align_up(Np * 4);
+    uint32_t* kb = (uint32_t*)sc; sc += align_up(Np * 4);
+    uint32_t* va = (uint32_t*)sc; sc += align_up(Np * 4);
+    uint32_t* vb = (uint32_t*)sc; sc += align_up(Np * 4);
+    uint32_t* ticket = (uint32_t*)sc; sc += 128;
+    DGS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st), "ticket memset");
+    const SortScratch ss = bind_sort_scratch(sc, (uint32_t)(Np / SORT_CHUNK), 8, ticket);
+    sort_uniform_u32(nseg, (uint32_t)len, (uint32_t)stride, keys, ka, va, kb, vb, ss, key_bits, st);
+    const size_t n = (size_t)nseg * len;
+    k_debug_unpad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nseg, (uint32_t)len, (uint32_t)stride, kb, vb, keys_sorted, index_sorted);
+    DGS_CUDA(cudaGetLastError(), "dgs_debug_sort");
     return DGS_OK;
 }
 

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
     const size_t pix_id = (size_t)f.W * pixy + pixx;
     const float pixfx = (float)pixx, pixfy = (float)pixy;
 
-    const uint2 range = p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile];
+    const uint2 range = decode_range(p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile]);
     const uint32_t a_xy = smem_addr(sm.xy), a_con = smem_addr(sm.con), a_rgbd = smem_addr(sm.rgbd);
     const uint32_t a_id = smem_addr(sm.id);
 

@@ -12,7 +12,6 @@
 // cannot reject it, instead of every thread re-reading every accepted box from global memory.
 #include "dgs_b200.h"
 #include "dgs_internal.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
 
 namespace dgs {
@@ -20,8 +19,8 @@ namespace dgs {
 #define KNN_BOX 256
 
 struct KnnLayout {
-    size_t bbox, codes, codes_sorted, idx, idx_sorted, pts, boxes, sort_temp, total;
-    size_t sort_temp_bytes;
+    size_t bbox, codes, keys_a, keys_b, vals_a, idx_sorted, pts, boxes, sort_scratch, ticket, total;
+    size_t stride;   // P rounded up to the sort's chunk
 };
 static KnnLayout knn_layout(size_t P)
 {
@@ -29,17 +28,17 @@ static KnnLayout knn_layout(size_t P)
     size_t o = 0;
     const size_t nb = (P + KNN_BOX - 1) / KNN_BOX;
     L.bbox = o; o = align_up(o + 8 * sizeof(float));
+    const size_t Pp = (P + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
+    L.stride = Pp;
     L.codes = o; o = align_up(o + P * sizeof(uint32_t));
-    L.codes_sorted = o; o = align_up(o + P * sizeof(uint32_t));
-    L.idx = o; o = align_up(o + P * sizeof(uint32_t));
-    L.idx_sorted = o; o = align_up(o + P * sizeof(uint32_t));
+    L.keys_a = o; o = align_up(o + Pp * sizeof(uint32_t));
+    L.keys_b = o; o = align_up(o + Pp * sizeof(uint32_t));
+    L.vals_a = o; o = align_up(o + Pp * sizeof(uint32_t));
+    L.idx_sorted = o; o = align_up(o + Pp * sizeof(uint32_t));
     L.pts = o; o = align_up(o + P * sizeof(float4));
     L.boxes = o; o = align_up(o + nb * 2 * sizeof(float4));
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int64_t)P);
-    L.sort_temp_bytes = tmp;
-    L.sort_temp = o; o = align_up(o + tmp);
+    L.sort_scratch = o; o = align_up(o + sort_scratch_bytes((uint32_t)(Pp / SORT_CHUNK), 8));
+    L.ticket = o; o = align_up(o + sizeof(uint32_t));
     L.total = o + 128;
     return L;
 }
@@ -89,7 +88,7 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x)
     return x;
 }
 __global__ void k_knn_morton(int P, const float* __restrict__ pts, const unsigned* __restrict__ bbox,
-                             uint32_t* __restrict__ codes, uint32_t* __restrict__ idx)
+                             uint32_t* __restrict__ codes)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -102,7 +101,6 @@ __global__ void k_knn_morton(int P, const float* __restrict__ pts, const unsigne
         c |= spread10((uint32_t)(nrm * 1023.0f)) << d;
     }
     codes[i] = c;
-    idx[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(KNN_BOX) k_knn_gather_boxes(int P, const float* __restrict__ pts,
@@ -206,28 +204,27 @@ int dgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scra
 {
     using namespace dgs;
     if (P <= 0) return DGS_OK;
-    if (!points || !mean_dist2 || !scratch) return DGS_ERR_INVALID_ARGUMENT;
+    if (!points || !mean_dist2 || !scratch) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_knn_mean_dist2: invalid argument");
     cudaStream_t st = (cudaStream_t)stream;
     const KnnLayout L = knn_layout((size_t)P);
     char* sc = (char*)(((uintptr_t)scratch + 127) & ~(uintptr_t)127);
     unsigned* bbox = (unsigned*)(sc + L.bbox);
     uint32_t* codes = (uint32_t*)(sc + L.codes);
-    uint32_t* codes_sorted = (uint32_t*)(sc + L.codes_sorted);
-    uint32_t* idx = (uint32_t*)(sc + L.idx);
     uint32_t* idx_sorted = (uint32_t*)(sc + L.idx_sorted);
     float4* pts = (float4*)(sc + L.pts);
     float4* boxes = (float4*)(sc + L.boxes);
     const int nb = (P + KNN_BOX - 1) / KNN_BOX;
     k_knn_bbox_init<<<1, 32, 0, st>>>(bbox);
     k_knn_bbox<<<min(1024, (P + 255) / 256), 256, 0, st>>>(P, points, bbox);
-    k_knn_morton<<<(P + 255) / 256, 256, 0, st>>>(P, points, bbox, codes, idx);
-    size_t tmp = L.sort_temp_bytes;
-    if (cub::DeviceRadixSort::SortPairs(sc + L.sort_temp, tmp, codes, codes_sorted, idx, idx_sorted, (int64_t)P, 0, 30,
-                                        st) != cudaSuccess)
-        return DGS_ERR_CUDA;
+    k_knn_morton<<<(P + 255) / 256, 256, 0, st>>>(P, points, bbox, codes);
+    // Morton order: the library's own segmented radix sort (dgs_binning.cu) with one segment; values = point index
+    if (cudaMemsetAsync(sc + L.ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return dgs::fail_cuda(cudaGetLastError(), "dgs_knn_mean_dist2");
+    const SortScratch ss = bind_sort_scratch(sc + L.sort_scratch, (uint32_t)(L.stride / SORT_CHUNK), 8, (uint32_t*)(sc + L.ticket));
+    sort_uniform_u32(1, (uint32_t)P, (uint32_t)L.stride, codes, (uint32_t*)(sc + L.keys_a), (uint32_t*)(sc + L.vals_a),
+                     (uint32_t*)(sc + L.keys_b), idx_sorted, ss, 30, st);
     k_knn_gather_boxes<<<nb, KNN_BOX, 0, st>>>(P, points, idx_sorted, pts, boxes);
     k_knn_search<<<nb, KNN_BOX, 0, st>>>(P, pts, boxes, mean_dist2);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_knn_mean_dist2"); }
 }
 
 }  // extern "C"

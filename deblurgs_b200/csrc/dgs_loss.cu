@@ -91,30 +91,30 @@ extern "C" {
 int dgs_blur_loss_forward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
                           float lambda_t_smooth, float* loss_out, double* scratch, void* stream)
 {
-    if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
-    if (!blurred || !gt || !loss_out || !scratch) return DGS_ERR_INVALID_ARGUMENT;
-    if (!subframes && lambda_t_smooth != 0.0f) return DGS_ERR_INVALID_ARGUMENT;   // NULL stack only with lambda = 0
+    if (F <= 0 || chw <= 0) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_forward: invalid argument");
+    if (!blurred || !gt || !loss_out || !scratch) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_forward: invalid argument");
+    if (!subframes && lambda_t_smooth != 0.0f) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_forward: invalid argument");   // NULL stack only with lambda = 0
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return DGS_ERR_CUDA;
+    if (cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return dgs::fail_cuda(cudaGetLastError(), "dgs_blur_loss_forward");
     const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
     dgs::k_blur_loss_fwd<<<blocks, 256, 0, st>>>(F, (size_t)chw, subframes, blurred, gt, scratch);
     dgs::k_blur_loss_finalize<<<1, 1, 0, st>>>(F, (size_t)chw, lambda_t_smooth, scratch, loss_out);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_blur_loss_forward"); }
 }
 
 int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const float* blurred, const float* gt,
                            float lambda_t_smooth, const float* grad_out, float* dL_dblurred,
                            float* dL_dsubframes, void* stream)
 {
-    if (F <= 0 || chw <= 0) return DGS_ERR_INVALID_ARGUMENT;
-    if (!blurred || !gt || !dL_dblurred) return DGS_ERR_INVALID_ARGUMENT;
-    if ((!subframes || !dL_dsubframes) && lambda_t_smooth != 0.0f) return DGS_ERR_INVALID_ARGUMENT;
+    if (F <= 0 || chw <= 0) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_backward: invalid argument");
+    if (!blurred || !gt || !dL_dblurred) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_backward: invalid argument");
+    if ((!subframes || !dL_dsubframes) && lambda_t_smooth != 0.0f) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_blur_loss_backward: invalid argument");
     if (!subframes) dL_dsubframes = nullptr;
     const int blocks = (int)((chw + 255) / 256 < 148 * 8 ? (chw + 255) / 256 : 148 * 8);
     dgs::k_blur_loss_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(F, (size_t)chw, subframes, blurred, gt,
                                                                     lambda_t_smooth, grad_out, dL_dblurred,
                                                                     dL_dsubframes);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_blur_loss_backward"); }
 }
 
 }  // extern "C"

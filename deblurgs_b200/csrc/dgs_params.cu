@@ -181,8 +181,6 @@ __global__ void __launch_bounds__(256) k_adam(const AdamBatch b)
 
 }  // namespace dgs
 
-extern "C" void dgs_profile_note(int stage, void* stream, int own_kernels, int begin, int* token);
-
 extern "C" {
 
 int dgs_activate_forward(int P, int sh_coeffs, const float* features_dc, const float* features_rest,
@@ -190,21 +188,21 @@ int dgs_activate_forward(int P, int sh_coeffs, const float* features_dc, const f
                          float scale_lower_bound, int isotropic,
                          float* shs, float* scales, float* rotations, float* opacities, void* stream)
 {
-    if (P < 0 || sh_coeffs < 1) return DGS_ERR_INVALID_ARGUMENT;
+    if (P < 0 || sh_coeffs < 1) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_activate_forward: invalid argument");
     if (P == 0) return DGS_OK;
     if (!features_dc || (sh_coeffs > 1 && !features_rest) || !scaling || !rotation || !opacity || !shs ||
         !scales || !rotations || !opacities)
-        return DGS_ERR_INVALID_ARGUMENT;
+        return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_activate_forward: invalid argument");
     const size_t total = (size_t)P * 3 * sh_coeffs;
     const size_t want = (total + 255) / 256;
     const int blocks = (int)(want < (size_t)148 * 16 ? want : (size_t)148 * 16);
-    int tok = -1;
-    dgs_profile_note(dgs::ST_ACTIVATE_FWD, stream, 1, 1, &tok);
-    dgs::k_activate_fwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, sh_coeffs, features_dc, features_rest, scaling,
-                                                                  rotation, opacity, scale_lower_bound, isotropic,
-                                                                  shs, scales, rotations, opacities);
-    dgs_profile_note(dgs::ST_ACTIVATE_FWD, stream, 0, 0, &tok);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    {
+        dgs::StageTimer timer(dgs::ST_ACTIVATE_FWD, (cudaStream_t)stream, 1);
+        dgs::k_activate_fwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, sh_coeffs, features_dc, features_rest, scaling,
+                                                                      rotation, opacity, scale_lower_bound, isotropic,
+                                                                      shs, scales, rotations, opacities);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_activate_forward"); }
 }
 
 int dgs_activate_backward(int P, int sh_coeffs, const float* scaling, const float* rotation, const float* opacity,
@@ -212,31 +210,31 @@ int dgs_activate_backward(int P, int sh_coeffs, const float* scaling, const floa
                           const float* dL_dopacities, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
                           float* dL_dscaling, float* dL_drotation, float* dL_dopacity, void* stream)
 {
-    if (P < 0 || sh_coeffs < 1) return DGS_ERR_INVALID_ARGUMENT;
+    if (P < 0 || sh_coeffs < 1) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_activate_backward: invalid argument");
     if (P == 0) return DGS_OK;
     if (!scaling || !rotation || !opacity || !dL_dfeatures_dc || (sh_coeffs > 1 && !dL_dfeatures_rest) ||
         !dL_dscaling || !dL_drotation || !dL_dopacity)
-        return DGS_ERR_INVALID_ARGUMENT;
+        return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_activate_backward: invalid argument");
     const size_t total = (size_t)P * 3 * sh_coeffs;
     const size_t want = (total + 255) / 256;
     const int blocks = (int)(want < (size_t)148 * 16 ? want : (size_t)148 * 16);
-    int tok = -1;
-    dgs_profile_note(dgs::ST_ACTIVATE_BWD, stream, 1, 1, &tok);
-    dgs::k_activate_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, sh_coeffs, scaling, rotation, opacity, isotropic,
-                                                                  dL_dshs, dL_dscales, dL_drotations, dL_dopacities,
-                                                                  dL_dfeatures_dc, dL_dfeatures_rest, dL_dscaling,
-                                                                  dL_drotation, dL_dopacity);
-    dgs_profile_note(dgs::ST_ACTIVATE_BWD, stream, 0, 0, &tok);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    {
+        dgs::StageTimer timer(dgs::ST_ACTIVATE_BWD, (cudaStream_t)stream, 1);
+        dgs::k_activate_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, sh_coeffs, scaling, rotation, opacity, isotropic,
+                                                                      dL_dshs, dL_dscales, dL_drotations, dL_dopacities,
+                                                                      dL_dfeatures_dc, dL_dfeatures_rest, dL_dscaling,
+                                                                      dL_drotation, dL_dopacity);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_activate_backward"); }
 }
 
 int dgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const int64_t* numel, const double* lr, const int64_t* step,
                   double beta1, double beta2, double eps, double clip_grad_value, void* stream)
 {
-    if (n_tensors < 0 || n_tensors > DGS_ADAM_MAX_TENSORS) return DGS_ERR_INVALID_ARGUMENT;
+    if (n_tensors < 0 || n_tensors > DGS_ADAM_MAX_TENSORS) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_adam_step: invalid argument");
     if (n_tensors == 0) return DGS_OK;
-    if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !lr || !step) return DGS_ERR_INVALID_ARGUMENT;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !lr || !step) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_adam_step: invalid argument");
     dgs::AdamBatch b;
     memset(&b, 0, sizeof(b));
     // scalars are formed in double and rounded once, as torch does with its Python floats
@@ -244,9 +242,9 @@ int dgs_adam_step(int n_tensors, float* const* params, const float* const* grads
     b.clip = (float)clip_grad_value;
     long long blocks = 0;
     for (int k = 0; k < n_tensors; k++) {
-        if (numel[k] < 0 || step[k] < 1) return DGS_ERR_INVALID_ARGUMENT;
+        if (numel[k] < 0 || step[k] < 1) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_adam_step: invalid argument");
         if (numel[k] == 0) continue;
-        if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k]) return DGS_ERR_INVALID_ARGUMENT;
+        if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k]) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_adam_step: invalid argument");
         dgs::AdamTensor& t = b.t[b.count++];
         t.p = params[k]; t.g = grads[k]; t.m = exp_avg[k]; t.v = exp_avg_sq[k];
         t.n = numel[k];
@@ -258,12 +256,12 @@ int dgs_adam_step(int n_tensors, float* const* params, const float* const* grads
         blocks += (numel[k] + ADAM_CHUNK - 1) / ADAM_CHUNK;
     }
     if (blocks == 0) return DGS_OK;
-    if (blocks > 0x7fffffffLL) return DGS_ERR_UNSUPPORTED;
-    int tok = -1;
-    dgs_profile_note(dgs::ST_ADAM, stream, 1, 1, &tok);
-    dgs::k_adam<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b);
-    dgs_profile_note(dgs::ST_ADAM, stream, 0, 0, &tok);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    if (blocks > 0x7fffffffLL) return dgs::fail(DGS_ERR_UNSUPPORTED, "dgs_adam_step: size not supported");
+    {
+        dgs::StageTimer timer(dgs::ST_ADAM, (cudaStream_t)stream, 1);
+        dgs::k_adam<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_adam_step"); }
 }
 
 }  // extern "C"

@@ -246,8 +246,6 @@ __global__ void k_pose_backward(int F, int C, const float* __restrict__ nu, cons
 
 }  // namespace dgs
 
-extern "C" void dgs_profile_note(int stage, void* stream, int own_kernels, int begin, int* token);
-
 extern "C" {
 
 int dgs_pose_forward(int F, int curve_order, const float* ctrl_trans, const float* ctrl_rot,
@@ -257,14 +255,14 @@ int dgs_pose_forward(int F, int curve_order, const float* ctrl_trans, const floa
     if (F <= 0) return DGS_OK;
     if (curve_order < 0 || curve_order > 64 || !ctrl_trans || !ctrl_rot || !nu || !proj_t || !viewmatrix ||
         !projmatrix || !campos)
-        return DGS_ERR_INVALID_ARGUMENT;
-    int tok = -1;
-    dgs_profile_note(dgs::ST_POSE_FWD, stream, 1, 1, &tok);
-    dgs::k_pose_forward<<<(F + 63) / 64, 64, 0, (cudaStream_t)stream>>>(F, curve_order, ctrl_trans, ctrl_rot, nu,
-                                                                        proj_t, viewmatrix, projmatrix, campos,
-                                                                        jacobian);
-    dgs_profile_note(dgs::ST_POSE_FWD, stream, 0, 0, &tok);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+        return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_forward: invalid argument");
+    {
+        dgs::StageTimer timer(dgs::ST_POSE_FWD, (cudaStream_t)stream, 1);
+        dgs::k_pose_forward<<<(F + 63) / 64, 64, 0, (cudaStream_t)stream>>>(F, curve_order, ctrl_trans, ctrl_rot, nu,
+                                                                            proj_t, viewmatrix, projmatrix, campos,
+                                                                            jacobian);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_pose_forward"); }
 }
 
 int dgs_pose_backward(int F, int curve_order, const float* ctrl_trans, const float* ctrl_rot,
@@ -273,15 +271,15 @@ int dgs_pose_backward(int F, int curve_order, const float* ctrl_trans, const flo
                       float* dL_dnu, void* stream)
 {
     (void)ctrl_trans; (void)ctrl_rot;
-    if (curve_order < 0 || curve_order > 64 || F < 0 || F > DGS_MAX_SUBFRAMES) return DGS_ERR_INVALID_ARGUMENT;
-    if (!dL_dctrl_trans || !dL_dctrl_rot) return DGS_ERR_INVALID_ARGUMENT;
-    if (F > 0 && (!nu || !jacobian || !dL_dviewmatrix || !dL_dprojmatrix)) return DGS_ERR_INVALID_ARGUMENT;
-    int tok = -1;
-    dgs_profile_note(dgs::ST_POSE_BWD, stream, 1, 1, &tok);
-    dgs::k_pose_backward<<<1, 128, (size_t)(F > 0 ? F : 1) * POSE_COLS * sizeof(double), (cudaStream_t)stream>>>(
-        F, curve_order, nu, jacobian, dL_dviewmatrix, dL_dprojmatrix, dL_dctrl_trans, dL_dctrl_rot, dL_dnu);
-    dgs_profile_note(dgs::ST_POSE_BWD, stream, 0, 0, &tok);
-    return cudaGetLastError() == cudaSuccess ? DGS_OK : DGS_ERR_CUDA;
+    if (curve_order < 0 || curve_order > 64 || F < 0 || F > DGS_MAX_SUBFRAMES) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_backward: invalid argument");
+    if (!dL_dctrl_trans || !dL_dctrl_rot) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_backward: invalid argument");
+    if (F > 0 && (!nu || !jacobian || !dL_dviewmatrix || !dL_dprojmatrix)) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_backward: invalid argument");
+    {
+        dgs::StageTimer timer(dgs::ST_POSE_BWD, (cudaStream_t)stream, 1);
+        dgs::k_pose_backward<<<1, 128, (size_t)(F > 0 ? F : 1) * POSE_COLS * sizeof(double), (cudaStream_t)stream>>>(
+            F, curve_order, nu, jacobian, dL_dviewmatrix, dL_dprojmatrix, dL_dctrl_trans, dL_dctrl_rot, dL_dnu);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_pose_backward"); }
 }
 
 }  // extern "C"

@@ -8,6 +8,7 @@ taekkii/deblurgs: `GaussianRasterizationSettings` (same 13 fields, same order, :
 `rasterize_blurry` that renders all F sub-frames of a blurry view in one call.
 """
 import ctypes as C
+import os
 from typing import NamedTuple
 
 import torch
@@ -66,10 +67,16 @@ def _require_cuda(t, name):
         raise _lib.DgsError("%s must be a CUDA tensor: libdgs_b200 has no CPU path" % name)
 
 
+# Expected number of (Gaussian, tile) duplicates per workload shape, learnt from the previous call: lets the
+# forward size its binning buffer without waiting for the device (dgs_blur_forward_hint).  The first call of a
+# shape (and every call with DGS_EXACT_BINNING=1) runs in exact mode with one host synchronisation.
+_CAPACITY_HINT = {}
+
+
 def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                      viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy, scale_modifier,
-                     z_near, z_far, sh_degree, prefiltered, use_sigmoid, want_blur, blur_denominator):
-    """Runs dgs_blur_forward. viewmatrix/projmatrix [F,4,4], campos [F,3]."""
+                     z_near, z_far, sh_degree, prefiltered, use_sigmoid, want_blur, blur_denominator, exact=False):
+    """Runs dgs_blur_forward_hint. viewmatrix/projmatrix [F,4,4], campos [F,3]."""
     lib = _lib.load()
     _require_cuda(means3D, "means3D")
     if means3D.dim() != 2 or means3D.shape[1] != 3:
@@ -91,8 +98,10 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
         if blur is not None:
             blur.zero_()
         return color, depth, radii, blur, 0, geom.t, binning.t, img.t
+    shape_key = (dev.index, P, F, H, W)
+    hint = 0 if (exact or os.environ.get("DGS_EXACT_BINNING") == "1") else _CAPACITY_HINT.get(shape_key, 0)
     with torch.cuda.device(dev):
-        rc = lib.dgs_blur_forward(
+        rc = lib.dgs_blur_forward_hint(
             geom.cb, None, binning.cb, None, img.cb, None,
             P, F, int(sh_degree), int(M),
             _lib.ptr(bg), int(W), int(H),
@@ -104,13 +113,15 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
             int(bool(prefiltered)), int(bool(use_sigmoid)),
             _lib.ptr(color), _lib.ptr(depth), _lib.ptr(radii),
             _lib.ptr(blur), float(blur_denominator),
-            C.byref(num_rendered), _stream_ptr(dev))
+            int(hint), C.byref(num_rendered), _stream_ptr(dev))
     # drop the ctypes callbacks: they close over the _Buffer objects (a reference cycle), and a cycle
     # would keep hundreds of MB of state buffers alive until Python's cyclic GC runs, forcing the caching
     # allocator to cudaMalloc fresh blocks every step in the meantime
     geom.cb = binning.cb = img.cb = None
-    _lib.check(rc, "dgs_blur_forward")
-    return color, depth, radii, blur, int(num_rendered.value), geom.t, binning.t, img.t
+    _lib.check(rc, "dgs_blur_forward_hint")
+    D = int(num_rendered.value)
+    _CAPACITY_HINT[shape_key] = D + D // 4 + 65536
+    return color, depth, radii, blur, D, geom.t, binning.t, img.t
 
 
 def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacities, scales, rotations,

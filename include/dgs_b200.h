@@ -86,6 +86,39 @@ int dgs_blur_forward(
     int64_t* num_rendered, void* stream);
 
 /*
+ * The same forward without a host synchronisation.  dgs_blur_forward has to learn the number of duplicates D
+ * on the host before it can size the binning buffer (one cudaStreamSynchronize per view; the reference does
+ * one per sub-frame, rasterizer_impl.cu:287).  Here the caller supplies `binning_capacity` = the number of
+ * duplicates it expects at most (e.g. 1.25 x the previous step's num_rendered); the buffer is sized from it,
+ * every kernel of the view is enqueued at once and D stays on the device.
+ *   num_rendered != NULL: after enqueuing, the host waits for a 24-byte status read-back that was issued right
+ *       after the scan stage (the GPU is busy with the blend meanwhile) and, if D exceeded the capacity, re-runs
+ *       the tile sort and the blend with the exact size: results are always complete, *num_rendered = D.
+ *   num_rendered == NULL: nothing is waited for (the call can be captured in a CUDA graph).  If D exceeds the
+ *       capacity the tile sort is skipped (all lists empty: background only); dgs_blur_forward_status reports
+ *       D and the overflow flag so that the caller can replay with a larger capacity.
+ * binning_capacity == 0 behaves like dgs_blur_forward.  The backward needs no D: pass num_rendered = -1.
+ */
+int dgs_blur_forward_hint(
+    dgs_alloc_fn geom_alloc, void* geom_ctx,
+    dgs_alloc_fn binning_alloc, void* binning_ctx,
+    dgs_alloc_fn image_alloc, void* image_ctx,
+    int P, int F, int sh_degree, int sh_coeffs,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far,
+    int prefiltered, int use_sigmoid,
+    float* out_color, float* out_depth, int* radii,
+    float* out_blur, float blur_denominator,
+    int64_t binning_capacity, int64_t* num_rendered, void* stream);
+/* D and the overflow flag of a forward call, read from its geometry buffer (synchronises the stream). */
+int dgs_blur_forward_status(const char* geom_buffer, int P, int F, int64_t* num_rendered, int* overflow,
+                            void* stream);
+
+/*
  * Batched backward.  dL_dpix [F,3,H,W], dL_dpixdepth [F,1,H,W] (either may be NULL = zeros);
  * dL_dblur [3,H,W] or NULL: gradient of the blurred image, folded in as dL_dpix[s] += dL_dblur /
  * blur_denominator for every sub-frame (the backward of the mean, without materialising [F,3,H,W]).
@@ -156,22 +189,30 @@ int dgs_backward(
  * reference's per-sub-frame quantities (GeometryState / BinningState / ImageState,
  * rasterizer_impl.h:31-63).  All outputs optional (NULL = skip).
  *   depths [F,P] means2D [F,P,2] conic_opacity [F,P,4] rgb [F,P,3] clamped [F,P,3]
- *   tiles_touched [F,P] u32   point_offsets [F*P] u32 (inclusive scan of tiles_touched over the whole batch
- *   taken in the library's depth-sorted entry order; its last element is num_rendered)
+ *   tiles_touched [F,P] u32   point_offsets [F,P] u32 (per sub-frame: inclusive scan of tiles_touched taken
+ *   in the library's depth-sorted order; element [s][P-1] is the sub-frame's num_rendered)
  */
 int dgs_debug_geometry(const char* geom_buffer, int P, int F,
                        float* depths, float* means2D, float* conic_opacity, float* rgb,
                        float* clamped, uint32_t* tiles_touched, uint32_t* point_offsets,
                        void* stream);
-/*   keys [D] u64 (batched key of every sorted list entry: sub-frame | tile | depth bits; the library
- *   sorts in two stages -- depth first, then a stable sort on sub-frame | tile -- so the 64-bit key
- *   is rebuilt here from the sorted 32-bit key and the entry's depth), point_list [D] u32 */
-int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, int P, int F, int width, int height,
-                      int64_t num_rendered, uint64_t* keys, uint32_t* point_list, void* stream);
-/*   ranges [F,tiles,2] u32 (absolute positions in the batched list), final_T [F,H,W],
- *   n_contrib [F,H,W] u32 */
+/*   keys [D] u64 (batched key of every sorted list entry: sub-frame | tile | depth bits; the library sorts in two
+ *   stages -- Gaussians by depth, then the generated duplicates by tile inside each sub-frame's segment -- so
+ *   the 64-bit key is rebuilt here from the entry's position and depth), point_list [D] u32, both compacted
+ *   (the library pads every sub-frame's list to a multiple of 4096); ranges [F,tiles,2] u32 = positions in
+ *   that compacted list */
+int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, const char* image_buffer, int P, int F,
+                      int width, int height, int64_t num_rendered, uint64_t* keys, uint32_t* point_list,
+                      uint32_t* ranges, void* stream);
+/*   final_T [F,H,W], n_contrib [F,H,W] u32 */
 int dgs_debug_image(const char* image_buffer, int F, int width, int height,
-                    uint32_t* ranges, float* final_T, uint32_t* n_contrib, void* stream);
+                    float* final_T, uint32_t* n_contrib, void* stream);
+/* The library's segmented LSD radix sort on its own (test hook): keys [nseg][len] u32 sorted on their low
+ * key_bits bits inside every segment, stable; keys_sorted / index_sorted [nseg][len] (either may be NULL).
+ * scratch: dgs_debug_sort_scratch_bytes(nseg, len). */
+size_t dgs_debug_sort_scratch_bytes(int nseg, int64_t len);
+int dgs_debug_sort(int nseg, int64_t len, int key_bits, const uint32_t* keys, uint32_t* keys_sorted,
+                   uint32_t* index_sorted, char* scratch, void* stream);
 /* Number of key bits used for the tile id and the sub-frame id of the batched sort key. */
 int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bits);
 
@@ -180,7 +221,7 @@ int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bit
  * dgs_profile_enable(1): every stage of the calls above is bracketed by a CUDA event pair on the
  * caller's stream.  dgs_profile_read synchronises those events and returns accumulated milliseconds
  * and call counts per stage (names from dgs_profile_stage_name).  dgs_launch_count = number of
- * kernels of THIS library launched so far (library scan/sort kernels are not counted).
+ * kernels of THIS library launched so far (every kernel on the path is the library's own).
  * dgs_debug_workload replays the compositing loop and writes {E, K, E_b} (list entries
  * evaluated, entries that contributed, entries replayed by the backward) to out_dev[3] (device).
  */

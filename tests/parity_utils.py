@@ -30,7 +30,7 @@ def make_inputs(name, device="cuda", sh_degree=3, P=None, F=None):
 
 
 def ours_forward(cam, scene, bg, view, proj, campos, sh_degree=None, use_sigmoid=False, colors_precomp=None,
-                 cov3D_precomp=None, scale_modifier=1.0, want_blur=True):
+                 cov3D_precomp=None, scale_modifier=1.0, want_blur=True, exact=False):
     sh_degree = scene.sh_degree if sh_degree is None else sh_degree
     shs = None if colors_precomp is not None else scene.shs
     scales = None if cov3D_precomp is not None else scene.scales
@@ -38,7 +38,7 @@ def ours_forward(cam, scene, bg, view, proj, campos, sh_degree=None, use_sigmoid
     out = rz._forward_batched(scene.means3D, shs, colors_precomp, scene.opacities, scales, rots, cov3D_precomp,
                               view, proj, campos, bg, cam.height, cam.width, cam.tanfovx, cam.tanfovy,
                               scale_modifier, 0.2, 100.0, sh_degree, False, use_sigmoid, want_blur,
-                              float(view.shape[0]))
+                              float(view.shape[0]), exact=exact)
     color, depth, radii, blur, D, geom, binning, img = out
     return dict(color=color, depth=depth, radii=radii, blur=blur, num_rendered=D, geom=geom, binning=binning,
                 img=img)
@@ -65,10 +65,10 @@ def ours_decode(fw, P, F, W, H):
         _lib.check(lib.dgs_debug_geometry(p(fw["geom"]), P, F, p(d["depths"]), p(d["means2D"]),
                                           p(d["conic_opacity"]), p(d["rgb"]), p(d["clamped"]),
                                           p(d["tiles_touched"]), p(d["point_offsets"]), st), "debug_geometry")
-    if D:
-        _lib.check(lib.dgs_debug_binning(p(fw["geom"]), p(fw["binning"]), P, F, W, H, D, p(d["keys"]), p(d["point_list"]), st), "debug_binning")
-    _lib.check(lib.dgs_debug_image(p(fw["img"]), F, W, H, p(d["ranges"]), p(d["final_T"]), p(d["n_contrib"]), st),
-               "debug_image")
+    if N:
+        _lib.check(lib.dgs_debug_binning(p(fw["geom"]), p(fw["binning"]), p(fw["img"]), P, F, W, H, D, p(d["keys"]),
+                                         p(d["point_list"]), p(d["ranges"]), st), "debug_binning")
+    _lib.check(lib.dgs_debug_image(p(fw["img"]), F, W, H, p(d["final_T"]), p(d["n_contrib"]), st), "debug_image")
     tb, sb = C.c_int(0), C.c_int(0)
     lib.dgs_key_bits(W, H, F, C.byref(tb), C.byref(sb))
     d["tile_bits"], d["subframe_bits"] = tb.value, sb.value
