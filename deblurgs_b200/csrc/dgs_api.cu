@@ -103,6 +103,7 @@ GeomLayout geom_layout(size_t P, size_t F)
     L.seg_start = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
     L.seg_len = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
     L.seg_adj = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
+    L.seg_total = o; o = align_up(o + (F + 1) * sizeof(unsigned long long));
     L.ticket = o; o = align_up(o + sizeof(uint32_t));
     L.rect = o; o = align_up(o + N * sizeof(uint2));
     L.dkeys = o; o = align_up(o + N * sizeof(uint32_t));
@@ -134,7 +135,7 @@ BinLayout bin_layout(size_t capacity, size_t F, size_t tiles)
     L.vals_a = o; if (L.passes >= 2) o = align_up(o + C * sizeof(uint32_t));
     L.keys_b = o; if (L.passes >= 3) o = align_up(o + C * sizeof(uint32_t));
     L.vals_b = o; if (L.passes >= 3) o = align_up(o + C * sizeof(uint32_t));
-    L.chunk_first = o; o = align_up(o + (chunks + 1) * sizeof(uint32_t));
+    L.chunk_first = o; o = align_up(o + (chunks + 1) * sizeof(uint2));
     L.sort_scratch = o; o = align_up(o + sort_scratch_bytes((uint32_t)chunks, L.bits));
     L.total = o + 128;
     return L;
@@ -210,6 +211,8 @@ static BinState bind_bin_state(char* geom, const GeomLayout& G)
     b.seg_start = (uint32_t*)(geom + G.seg_start);
     b.seg_len = (uint32_t*)(geom + G.seg_len);
     b.seg_adj = (uint32_t*)(geom + G.seg_adj);
+    b.seg_total = (unsigned long long*)(geom + G.seg_total);
+    b.ticket = (uint32_t*)(geom + G.ticket);
     return b;
 }
 
@@ -352,21 +355,21 @@ static int blur_forward_impl(
         if (!bin) return fail(DGS_ERR_ALLOC, "binning buffer allocation failed");
         bin = aligned128(bin);
         uint32_t* point_list = (uint32_t*)(bin + B.point_list);
-        uint32_t* chunk_first = (uint32_t*)(bin + B.chunk_first);
+        uint2* chunk_tab = (uint2*)(bin + B.chunk_first);
 
         if (F > 0 && tiles > 0)
             DGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)F * tiles * sizeof(uint2), st), "ranges memset");
         if (N > 0 && B.capacity > 0) {
-            { StageTimer t(ST_SCAN, st, 1); launch_entry_offsets(p, bs, chunk_first, st); }
+            { StageTimer t(ST_SCAN, st, 1); launch_entry_offsets(p, bs, chunk_tab, st); }
             // stage 2: duplicates generated from the depth-ordered entries and sorted by tile id inside every
             // sub-frame's segment; the last pass writes point_list and the per-tile ranges
             StageTimer t(ST_TILE_SORT, st, 3 * B.passes);
             SegTable tab;
             memset(&tab, 0, sizeof(tab));
             tab.seg_start = bs.seg_start; tab.seg_len = bs.seg_len; tab.seg_adj = bs.seg_adj;
-            tab.n_chunks = &bs.status->n_chunks; tab.nseg = F;
+            tab.n_chunks = &bs.status->n_chunks; tab.chunk_tab = chunk_tab; tab.nseg = F;
             GenParams gp;
-            gp.off = bs.off; gp.rec = bs.rec; gp.chunk_first = chunk_first;
+            gp.off = bs.off; gp.rec = bs.rec;
             gp.entries_per_seg = (uint32_t)P; gp.entry_stride = bs.stride; gp.tiles_x = p.tiles_x;
             const uint32_t max_chunks = (uint32_t)(B.capacity / SORT_CHUNK);
             const SortScratch sc = bind_sort_scratch(bin + B.sort_scratch, max_chunks, B.bits, ticket);

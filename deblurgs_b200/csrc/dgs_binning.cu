@@ -21,7 +21,7 @@
 //
 // Every pass is reduce-then-scan (k_sort_upsweep -> k_scan_counters -> k_sort_downsweep): per-chunk digit
 // histograms, one exclusive scan over the [segment][digit][chunk] counter matrix, then a stable scatter that
-// ranks 4096 items per block with warp-level match_any, reorders them in shared memory and writes runs.
+// ranks 2048 items per block with warp-level match_any, reorders them in shared memory and writes runs.
 // No spin-waiting anywhere (the scan uses a last-block-done ticket), so a kernel can never hang on
 // block-scheduling order.
 #include "dgs_internal.cuh"
@@ -41,6 +41,7 @@ struct ChunkInfo {
     uint32_t cbase;    // flat index of the segment's first chunk
     uint32_t start;    // seg_start[s]
     uint32_t adj;      // seg_start[s] - (number of items in earlier segments)
+    uint32_t first_entry;   // stage 2: first depth-ordered entry owning a duplicate of the chunk
 };
 
 __device__ __forceinline__ ChunkInfo locate_chunk(const SegTable& t, uint32_t b)
@@ -54,23 +55,22 @@ __device__ __forceinline__ ChunkInfo locate_chunk(const SegTable& t, uint32_t b)
         ci.cbase = ci.s * per;
         ci.start = ci.s * t.uni_stride;
         ci.adj = ci.s * (t.uni_stride - t.uni_len);
+        ci.first_entry = 0u;
         const uint32_t done = ci.c * SORT_CHUNK;
         ci.nv = t.uni_len > done ? min((uint32_t)SORT_CHUNK, t.uni_len - done) : 0u;
     } else {
-        const uint32_t pos = b * SORT_CHUNK;
-        int lo = 0, hi = t.nseg - 1;          // last s with seg_start[s] <= pos (empty segments share a start
-        while (lo < hi) {                      // with their successor and are skipped by taking the last)
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(t.seg_start + mid) <= pos) lo = mid; else hi = mid - 1;
-        }
-        ci.s = (uint32_t)lo;
-        ci.start = __ldg(t.seg_start + lo);
-        const uint32_t next = __ldg(t.seg_start + lo + 1);
+        // one 8-B load of the chunk table (written by k_entry_offsets), then three independent loads
+        const uint2 ct = __ldg(t.chunk_tab + b);
+        ci.first_entry = ct.x;
+        ci.s = ct.y;
+        ci.start = __ldg(t.seg_start + ci.s);
+        const uint32_t next = __ldg(t.seg_start + ci.s + 1);
+        const uint32_t len = __ldg(t.seg_len + ci.s);
+        ci.adj = __ldg(t.seg_adj + ci.s);
         ci.cbase = ci.start / SORT_CHUNK;
         ci.nch = (next - ci.start) / SORT_CHUNK;
         ci.c = b - ci.cbase;
-        ci.adj = __ldg(t.seg_adj + lo);
-        const uint32_t len = __ldg(t.seg_len + lo), done = ci.c * SORT_CHUNK;
+        const uint32_t done = ci.c * SORT_CHUNK;
         ci.nv = len > done ? min((uint32_t)SORT_CHUNK, len - done) : 0u;
     }
     return ci;
@@ -84,46 +84,74 @@ __device__ __forceinline__ uint32_t total_chunks(const SegTable& t)
 // ---------------------------------------------------------------------------------------------------
 // Generation of the stage-2 items (duplicateWithKeys, rasterizer_impl.cu:70-111, fused into the sort).
 // The chunk covers duplicates [r0, r1) of its sub-frame's depth-ordered emission; entry i owns
-// [off[i-1], off[i]) and enumerates the tiles of its rectangle row-major, like the reference.  A warp takes
-// 32 consecutive entries at a time (coalesced loads of offsets and packed rectangles) and then walks them
-// one after the other with all lanes spread over the entry's tiles.
+// [off[i-1], off[i]) and enumerates the tiles of its rectangle row-major, like the reference.  The inclusive
+// offsets of the chunk's entries (at most one entry per duplicate) are staged in shared memory; every thread
+// then finds the owner of each of its items by binary search.  Its items are 32 duplicates apart and every
+// entry owns at least one duplicate, so the owner moves by at most 32 entries from one item to the next: after
+// the first item the search window is 33 entries wide.
 // ---------------------------------------------------------------------------------------------------
-template <class Emit>
-__device__ __forceinline__ void expand_chunk(const GenParams& gp, const ChunkInfo& ci, uint32_t chunk_flat,
-                                             unsigned warp, unsigned lane, Emit emit)
+__device__ __forceinline__ void generate_items(const GenParams& gp, const ChunkInfo& ci, uint32_t* s_off /*[SORT_CHUNK + 32]*/,
+                                               unsigned tid, unsigned warp, unsigned lane, uint32_t (&tile)[SORT_ITEMS],
+                                               uint32_t (&gid)[SORT_ITEMS])
 {
     const uint32_t r0 = ci.c * SORT_CHUNK, r1 = r0 + ci.nv;
     const size_t seg = (size_t)ci.s * gp.entry_stride;
     const uint32_t* __restrict__ off = gp.off + seg;
     const uint2* __restrict__ rec = gp.rec + seg;
-    const uint32_t i0 = gp.chunk_first[chunk_flat];
-    for (uint32_t base = i0 + warp * 32u;; base += SORT_WARPS * 32u) {
-        const uint32_t i = base + lane;
-        uint32_t incl = 0xFFFFFFFFu, excl = 0xFFFFFFFFu;
-        uint2 r = make_uint2(0u, 0u);
-        if (i < gp.entries_per_seg) {
-            incl = off[i];
-            excl = i ? off[i - 1] : 0u;
-            r = rec[i];
+    const uint32_t i0 = ci.first_entry;
+    const uint32_t excl0 = i0 ? __ldg(off + i0 - 1) : 0u;
+    // s_off[k] = inclusive offset of entry i0 + k, staged until one reaches the end of the chunk; the 32 slots behind
+    // the last staged entry are filled with "infinity" so that the window reads below need no bound checks
+    uint32_t staged = SORT_CHUNK;
+    for (uint32_t k0 = 0; k0 < SORT_CHUNK; k0 += SORT_THREADS) {
+        const uint32_t k = k0 + tid, i = i0 + k;
+        const uint32_t v = i < gp.entries_per_seg ? __ldg(off + i) : 0xFFFFFFFFu;
+        s_off[k] = v;
+        if (__syncthreads_or(v >= r1)) { staged = k0 + SORT_THREADS; break; }
+    }
+    if (tid < 32) s_off[staged + tid] = 0xFFFFFFFFu;
+    __syncthreads();
+
+    // owner of the warp's first duplicate: binary search (warp-uniform); its index is at most the duplicate's
+    const uint32_t jw = warp * (32 * SORT_ITEMS);
+    uint32_t eA = 0;
+    if (jw < ci.nv) {
+        uint32_t lo = 0, hi = min(jw, staged - 1);
+        const uint32_t d = r0 + jw;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] > d) hi = mid; else lo = mid + 1;
         }
-        if (__shfl_sync(FULL_MASK, excl, 0) >= r1) break;     // this and every later group start behind the chunk
-        unsigned m = __ballot_sync(FULL_MASK, excl < r1 && incl > r0 && incl > excl);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t e_excl = __shfl_sync(FULL_MASK, excl, l), e_incl = __shfl_sync(FULL_MASK, incl, l);
-            const uint32_t rx = __shfl_sync(FULL_MASK, r.x, l), g = __shfl_sync(FULL_MASK, r.y, l);
-            const uint32_t x0 = rx & 1023u, y0 = (rx >> 10) & 1023u, w = ((rx >> 20) & 1023u) + 1u;
-            const uint32_t ja = max(e_excl, r0) - e_excl, jb = min(e_incl, r1) - e_excl;
-            const float wf = (float)w;
-            for (uint32_t j = ja + lane; j < jb; j += 32u) {
-                // row-major over the rectangle; (j + 0.5) / w is never within 0.5 / w of an integer, so the float
-                // quotient (2 ulp) truncates to floor(j / w) exactly for any rectangle of a <= 16K x 16K image
-                const uint32_t row = (uint32_t)__fdividef((float)j + 0.5f, wf);
-                const uint32_t tile = (y0 + row) * (uint32_t)gp.tiles_x + x0 + (j - row * w);
-                emit(e_excl + j - r0, tile, g);
-            }
+        eA = lo;
+    }
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; it++) {
+        // The 32 lanes hold 32 consecutive duplicates d0 .. d0+31; eA owns d0.  Every entry owns at least one
+        // duplicate, so the owners are eA .. eA+31 at most: lane l looks at where entry eA+l+1 STARTS (= the inclusive
+        // offset of eA+l); starts inside (d0, d0+31] become head bits, and a duplicate's owner is eA + the number
+        // of heads at or before it.
+        const uint32_t j = jw + it * 32 + lane;
+        const uint32_t d0 = r0 + jw + it * 32;
+        const uint32_t start_next = s_off[eA + lane];                 // start of entry eA + lane + 1
+        const uint32_t rel = start_next - d0;                         // > 0 for lane 0 because eA owns d0
+        const unsigned heads = __reduce_or_sync(FULL_MASK, rel < 32u ? (1u << rel) : 0u);
+        const uint32_t e = eA + __popc(heads & (0xFFFFFFFFu >> (31u - lane)));
+        tile[it] = 0u;
+        gid[it] = 0u;
+        if (j < ci.nv) {
+            const uint32_t excl = e ? s_off[e - 1] : excl0;
+            const uint2 r = __ldg(rec + i0 + e);
+            const uint32_t x0 = r.x & 1023u, y0 = (r.x >> 10) & 1023u, w = ((r.x >> 20) & 1023u) + 1u;
+            const uint32_t jj = d0 + lane - excl;
+            // row-major over the rectangle; (jj + 0.5) / w is never within 0.5 / w of an integer, so the float
+            // quotient (2 ulp) truncates to floor(jj / w) exactly for any rectangle of a <= 16K x 16K image
+            const uint32_t row = (uint32_t)__fdividef((float)jj + 0.5f, (float)w);
+            tile[it] = (y0 + row) * (uint32_t)gp.tiles_x + x0 + (jj - row * w);
+            gid[it] = r.y;
         }
+        // owner of the next round's first duplicate d0 + 32: the last lane's owner, or its successor if that entry ends here
+        const uint32_t e31 = eA + __popc(heads);
+        eA = e31 + (s_off[e31] <= d0 + 32u ? 1u : 0u);
     }
 }
 
@@ -137,22 +165,33 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_upsweep(const SegTable t,
 {
     constexpr int BINS = 1 << BITS;
     __shared__ uint32_t hist[SORT_WARPS][BINS];
+    __shared__ uint32_t s_off[GEN ? SORT_CHUNK + 32 : 1];
     if (blockIdx.x >= total_chunks(t)) return;
     const ChunkInfo ci = locate_chunk(t, blockIdx.x);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&hist[0][0])[k] = 0u;
-    __syncthreads();
     if (GEN) {
-        expand_chunk(gp, ci, blockIdx.x, warp, lane, [&](uint32_t, uint32_t tile, uint32_t) {
-            atomicAdd(&hist[warp][(tile >> shift) & (BINS - 1)], 1u);
-        });
+        uint32_t tile[SORT_ITEMS], gid[SORT_ITEMS];
+        generate_items(gp, ci, s_off, tid, warp, lane, tile, gid);      // contains barriers: hist is zeroed
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {
+            const uint32_t j = warp * (32 * SORT_ITEMS) + i * 32 + lane;
+            if (j < ci.nv) atomicAdd(&hist[warp][(tile[i] >> shift) & (BINS - 1)], 1u);
+        }
     } else {
+        __syncthreads();
         const uint32_t* __restrict__ src =
             keys_in + (in_seg_stride ? (size_t)ci.s * in_seg_stride : (size_t)ci.start) + (size_t)ci.c * SORT_CHUNK;
+        uint32_t k[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; i++) {           // all loads in flight before the first histogram update
+            const uint32_t j = i * SORT_THREADS + tid;
+            k[i] = j < ci.nv ? __ldg(src + j) : 0u;
+        }
 #pragma unroll
         for (int i = 0; i < SORT_ITEMS; i++) {
             const uint32_t j = i * SORT_THREADS + tid;
-            if (j < ci.nv) atomicAdd(&hist[warp][(src[j] >> shift) & (BINS - 1)], 1u);
+            if (j < ci.nv) atomicAdd(&hist[warp][(k[i] >> shift) & (BINS - 1)], 1u);
         }
     }
     __syncthreads();
@@ -204,11 +243,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scan_counters(uint32_t* __rest
     const uint32_t n_slices = (n + SCAN_SLICE - 1) / SCAN_SLICE;
     if (blockIdx.x >= n_slices) return;
     const unsigned tid = threadIdx.x;
-    const uint32_t base = blockIdx.x * SCAN_SLICE + tid * SORT_ITEMS;     // blocked: 16 consecutive counters per thread
-    uint32_t v[SORT_ITEMS];
+    const uint32_t base = blockIdx.x * SCAN_SLICE + tid * SCAN_ITEMS;     // blocked: 16 consecutive counters per thread
+    uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
 #pragma unroll
-    for (int q = 0; q < SORT_ITEMS / 4; q++) {
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
         uint4 x = make_uint4(0u, 0u, 0u, 0u);
         const uint32_t i = base + 4 * q;
         if (i + 3 < n) x = *reinterpret_cast<const uint4*>(data + i);
@@ -220,11 +259,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scan_counters(uint32_t* __rest
         v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++) { const uint32_t x = v[i]; v[i] = sum; sum += x; }
+    for (int i = 0; i < SCAN_ITEMS; i++) { const uint32_t x = v[i]; v[i] = sum; sum += x; }
     uint32_t total;
     const uint32_t ex = block_exclusive_scan_256(sum, s_warp, tid, total);
 #pragma unroll
-    for (int q = 0; q < SORT_ITEMS / 4; q++) {
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
         const uint32_t i = base + 4 * q;
         const uint4 x = make_uint4(v[4 * q] + ex, v[4 * q + 1] + ex, v[4 * q + 2] + ex, v[4 * q + 3] + ex);
         if (i + 3 < n) *reinterpret_cast<uint4*>(data + i) = x;
@@ -269,15 +308,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scan_counters(uint32_t* __rest
 //   ranges[t] = (~start, end) accumulated with atomicMax over the chunks that hold a piece of the run.
 // ---------------------------------------------------------------------------------------------------
 template <int BITS, bool GEN, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(
+__global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_downsweep(
     const SegTable t, const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t in_seg_stride,
     int shift, const uint32_t* __restrict__ counters, const uint32_t* __restrict__ slice_base,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const GenParams gp, uint2* __restrict__ ranges,
     uint32_t tiles_per_seg)
 {
     constexpr int BINS = 1 << BITS;
-    __shared__ uint32_t s_keys[SORT_CHUNK];
-    __shared__ uint32_t s_vals[SORT_CHUNK];
+    __shared__ uint32_t s_keys[2 * SORT_CHUNK];          // keys | values; GEN: first the staged entry offsets
+    uint32_t* const s_vals = s_keys + SORT_CHUNK;
     __shared__ uint32_t s_wc[SORT_WARPS][BINS + 1];      // per-warp digit counters (+1: invalid items)
     __shared__ uint32_t s_gdelta[BINS];                  // global position - block-local sorted position, per digit
     __shared__ uint32_t s_scan[SORT_WARPS + 1];
@@ -285,21 +324,17 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(
     const ChunkInfo ci = locate_chunk(t, blockIdx.x);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
+    // global base of this chunk's digit `tid` (scanned counter + slice base): requested now, used after the ranking
+    uint32_t gbase = 0;
+    if (tid < BINS) {
+        const size_t ci_idx = (size_t)ci.cbase * BINS + (size_t)tid * ci.nch + ci.c;
+        gbase = __ldg(counters + ci_idx) + __ldg(slice_base + ci_idx / SCAN_SLICE) + ci.adj;
+    }
     for (int k = tid; k < SORT_WARPS * (BINS + 1); k += SORT_THREADS) (&s_wc[0][0])[k] = 0u;
 
     uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
     if (GEN) {
-        expand_chunk(gp, ci, blockIdx.x, warp, lane, [&](uint32_t pos, uint32_t tile, uint32_t g) {
-            s_keys[pos] = tile;
-            s_vals[pos] = g;
-        });
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < SORT_ITEMS; i++) {
-            const uint32_t j = warp * (32 * SORT_ITEMS) + i * 32 + lane;
-            key[i] = s_keys[j];
-            val[i] = s_vals[j];
-        }
+        generate_items(gp, ci, s_keys, tid, warp, lane, key, val);
     } else {
         const size_t in0 = (in_seg_stride ? (size_t)ci.s * in_seg_stride : (size_t)ci.start) + (size_t)ci.c * SORT_CHUNK;
 #pragma unroll
@@ -313,26 +348,41 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(
             }
         }
     }
-    __syncthreads();     // counters zeroed; GEN: every thread has read its items (s_keys / s_vals are reused below)
+    __syncthreads();     // counters zeroed; GEN: the staged offsets are dead (s_keys is reused below)
 
-    // ---- rank inside the warp
+    // ---- rank inside the warp.  Which lanes share my digit: one ballot per digit bit (the match.any instruction
+    // iterates over the distinct values of the warp, up to 32 of them for a random 8-bit digit; ballots do not).
+    unsigned peers[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t j = warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        const uint32_t d = (key[i] >> shift) & (BINS - 1);
+        unsigned m = __ballot_sync(FULL_MASK, j < ci.nv);          // invalid items (tail of a segment) rank nowhere
+#pragma unroll
+        for (int b = 0; b < BITS; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned v = __ballot_sync(FULL_MASK, bit);
+            m &= bit ? v : ~v;
+        }
+        peers[i] = m;
+    }
+    // One shared-memory atomic per (round, digit group), issued by the group's lowest lane.  The rounds are issued
+    // in order by the converged warp and atomics on one address are applied in issue order, so nobody has to wait
+    // for a returned value before the next round goes out: the eight round trips overlap.
     uint32_t rank[SORT_ITEMS];
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         const uint32_t j = warp * (32 * SORT_ITEMS) + i * 32 + lane;
-        const uint32_t d = j < ci.nv ? ((key[i] >> shift) & (BINS - 1)) : (uint32_t)BINS;
-        const unsigned peers = __match_any_sync(FULL_MASK, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if ((int)lane == leader) {
-            old = s_wc[warp][d];
-            s_wc[warp][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(FULL_MASK, old, leader);
-        rank[i] = old + __popc(peers & lt_mask);
+        const uint32_t d = (key[i] >> shift) & (BINS - 1);
+        rank[i] = 0u;
+        if (j < ci.nv && lane == (unsigned)(__ffs(peers[i]) - 1))
+            rank[i] = atomicAdd(&s_wc[warp][d], (uint32_t)__popc(peers[i]));
         __syncwarp();
     }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++)   // (invalid lanes: peers may be empty, source lane 31 & garbage -- never used)
+        rank[i] = __shfl_sync(FULL_MASK, rank[i], (__ffs(peers[i]) - 1) & 31) + __popc(peers[i] & lt_mask);
     __syncthreads();
 
     // ---- per digit: counts of the warps -> exclusive prefix over the warps; digit totals -> block-local starts
@@ -344,9 +394,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(
     uint32_t chunk_total;
     const uint32_t bin_start = block_exclusive_scan_256(tot, s_scan, tid, chunk_total);
     if (tid < BINS) {
-        const size_t ci_idx = (size_t)ci.cbase * BINS + (size_t)tid * ci.nch + ci.c;
-        const uint32_t g = counters[ci_idx] + slice_base[ci_idx / SCAN_SLICE] + ci.adj;
-        s_gdelta[tid] = g - bin_start;
+        s_gdelta[tid] = gbase - bin_start;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) s_wc[w][tid] += bin_start;
     }
@@ -528,67 +576,73 @@ __global__ void __launch_bounds__(256) k_entry_gather(int P, uint32_t stride, co
     }
 }
 
-// one block: per-segment exclusive scan of the block sums, then the segment table and the status words
-__global__ void __launch_bounds__(1024) k_seg_scan(int nseg, uint32_t nb, const unsigned long long* __restrict__ block_sums,
-                                                   uint32_t* __restrict__ block_excl, BinStatus* __restrict__ status,
-                                                   uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
-                                                   uint32_t* __restrict__ seg_adj, unsigned long long capacity)
+// one block per segment: exclusive scan of the segment's block sums; the last block to finish (ticket) builds the
+// segment table and the status words from the segment totals
+__global__ void __launch_bounds__(256) k_seg_scan(int nseg, uint32_t nb, const unsigned long long* __restrict__ block_sums,
+                                                  uint32_t* __restrict__ block_excl, BinStatus* __restrict__ status,
+                                                  uint32_t* __restrict__ seg_start, uint32_t* __restrict__ seg_len,
+                                                  uint32_t* __restrict__ seg_adj, unsigned long long* __restrict__ seg_total,
+                                                  uint32_t* ticket, unsigned long long capacity)
 {
-    __shared__ unsigned long long s_warp[33];
-    __shared__ unsigned long long s_total[DGS_MAX_SUBFRAMES];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ bool s_last;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    for (int s = 0; s < nseg; s++) {
-        unsigned long long carry = 0;
-        for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
-            const uint32_t b = b0 + tid;
-            const unsigned long long v = b < nb ? block_sums[(size_t)s * nb + b] : 0ull;
-            unsigned long long inc = v;
+    const int s = blockIdx.x;
+    unsigned long long carry = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 256) {
+        const uint32_t b = b0 + tid;
+        const unsigned long long v = b < nb ? block_sums[(size_t)s * nb + b] : 0ull;
+        unsigned long long inc = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long o = __shfl_up_sync(FULL_MASK, inc, d);
-                if (lane >= (unsigned)d) inc += o;
-            }
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long acc = 0;
-                for (int w = 0; w < 32; w++) { const unsigned long long x = s_warp[w]; s_warp[w] = acc; acc += x; }
-                s_warp[32] = acc;
-            }
-            __syncthreads();
-            if (b < nb) block_excl[(size_t)s * nb + b] = (uint32_t)(carry + s_warp[warp] + inc - v);
-            carry += s_warp[32];
-            __syncthreads();
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(FULL_MASK, inc, d);
+            if (lane >= (unsigned)d) inc += o;
         }
-        if (tid == 0) s_total[s] = carry;
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long acc = 0;
+            for (int w = 0; w < 8; w++) { const unsigned long long x = s_warp[w]; s_warp[w] = acc; acc += x; }
+            s_warp[8] = acc;
+        }
+        __syncthreads();
+        if (b < nb) block_excl[(size_t)s * nb + b] = (uint32_t)(carry + s_warp[warp] + inc - v);
+        carry += s_warp[8];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seg_total[s] = carry;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == (unsigned)nseg - 1u;
     }
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long D = 0, padded = 0;
-        bool too_big = false;
-        for (int s = 0; s < nseg; s++) {
-            const unsigned long long len = s_total[s];
-            if (len >= 0xFFFFFFFFull) too_big = true;
-            seg_start[s] = (uint32_t)padded;
-            seg_len[s] = (uint32_t)len;
-            seg_adj[s] = (uint32_t)(padded - D);
-            D += len;
-            padded += (len + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
-        }
-        seg_start[nseg] = (uint32_t)padded;
-        const bool overflow = too_big || padded > capacity || padded >= 0xFFFFFFFFull;
-        status->num_rendered = D;
-        status->padded = padded;
-        status->overflow = overflow ? 1u : 0u;
-        status->n_chunks = overflow ? 0u : (uint32_t)(padded / SORT_CHUNK);   // overflow: stage 2 does nothing
+    if (!s_last || tid != 0) return;
+    __threadfence();
+    unsigned long long D = 0, padded = 0;
+    bool too_big = false;
+    for (int q = 0; q < nseg; q++) {
+        const unsigned long long len = __ldcg(seg_total + q);
+        if (len >= 0xFFFFFFFFull) too_big = true;
+        seg_start[q] = (uint32_t)padded;
+        seg_len[q] = (uint32_t)len;
+        seg_adj[q] = (uint32_t)(padded - D);
+        D += len;
+        padded += (len + SORT_CHUNK - 1) / SORT_CHUNK * SORT_CHUNK;
     }
+    seg_start[nseg] = (uint32_t)padded;
+    const bool overflow = too_big || padded > capacity || padded >= 0xFFFFFFFFull;
+    status->num_rendered = D;
+    status->padded = padded;
+    status->overflow = overflow ? 1u : 0u;
+    status->n_chunks = overflow ? 0u : (uint32_t)(padded / SORT_CHUNK);   // overflow: stage 2 does nothing
+    *ticket = 0u;
 }
 
 __global__ void __launch_bounds__(256) k_entry_offsets(int P, uint32_t stride, const uint32_t* __restrict__ cnt_sorted,
                                                        const uint32_t* __restrict__ block_excl,
                                                        const uint32_t* __restrict__ seg_start,
                                                        const BinStatus* __restrict__ status, uint32_t* __restrict__ off,
-                                                       uint32_t* __restrict__ chunk_first)
+                                                       uint2* __restrict__ chunk_tab)
 {
     __shared__ uint32_t s_scan[SORT_WARPS + 1];
     if (status->overflow) return;
@@ -617,7 +671,7 @@ __global__ void __launch_bounds__(256) k_entry_offsets(int P, uint32_t stride, c
         if (c[k] != 0u) {
             // chunk boundaries q * CHUNK inside [excl, run): this entry owns the first duplicate of chunk q
             for (uint32_t q = (excl + SORT_CHUNK - 1) / SORT_CHUNK; (unsigned long long)q * SORT_CHUNK < run; q++)
-                chunk_first[cbase + q] = i0 + k;
+                chunk_tab[cbase + q] = make_uint2(i0 + k, (uint32_t)s);
         }
     }
     uint32_t* dst = off + (size_t)s * stride;
@@ -634,15 +688,15 @@ void launch_entry_scan(const FwdParams& p, const BinState& b, unsigned long long
     const uint32_t nb = (uint32_t)((p.P + ENT_BLOCK - 1) / ENT_BLOCK);
     dim3 grid(nb, p.F);
     k_entry_gather<<<grid, 256, 0, st>>>(p.P, b.stride, b.order, p.rect, b.cnt_sorted, b.rec, b.block_sums);
-    k_seg_scan<<<1, 1024, 0, st>>>(p.F, nb, b.block_sums, b.block_excl, b.status, b.seg_start, b.seg_len, b.seg_adj,
-                                   capacity);
+    k_seg_scan<<<p.F, 256, 0, st>>>(p.F, nb, b.block_sums, b.block_excl, b.status, b.seg_start, b.seg_len, b.seg_adj,
+                                    b.seg_total, b.ticket, capacity);
 }
-void launch_entry_offsets(const FwdParams& p, const BinState& b, uint32_t* chunk_first, cudaStream_t st)
+void launch_entry_offsets(const FwdParams& p, const BinState& b, uint2* chunk_tab, cudaStream_t st)
 {
     const uint32_t nb = (uint32_t)((p.P + ENT_BLOCK - 1) / ENT_BLOCK);
     dim3 grid(nb, p.F);
     k_entry_offsets<<<grid, 256, 0, st>>>(p.P, b.stride, b.cnt_sorted, b.block_excl, b.seg_start, b.status, b.off,
-                                          chunk_first);
+                                          chunk_tab);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -71,6 +71,8 @@ def _require_cuda(t, name):
 # forward size its binning buffer without waiting for the device (dgs_blur_forward_hint).  The first call of a
 # shape (and every call with DGS_EXACT_BINNING=1) runs in exact mode with one host synchronisation.
 _CAPACITY_HINT = {}
+_KEEP_SCRATCH = False
+_last_scratch = None
 
 
 def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -168,6 +170,9 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
             _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
             _lib.ptr(dview), _lib.ptr(dproj), _lib.ptr(stats), _stream_ptr(dev))
     _lib.check(rc, "dgs_blur_backward")
+    if _KEEP_SCRATCH:   # test hook: the per-(sub-frame, Gaussian) screen-space gradients the blend backward produced
+        global _last_scratch
+        _last_scratch = scratch
     return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, stats
 
 

@@ -199,7 +199,7 @@ int dgs_debug_geometry(const char* geom_buffer, int P, int F,
 /*   keys [D] u64 (batched key of every sorted list entry: sub-frame | tile | depth bits; the library sorts in two
  *   stages -- Gaussians by depth, then the generated duplicates by tile inside each sub-frame's segment -- so
  *   the 64-bit key is rebuilt here from the entry's position and depth), point_list [D] u32, both compacted
- *   (the library pads every sub-frame's list to a multiple of 4096); ranges [F,tiles,2] u32 = positions in
+ *   (the library pads every sub-frame's list to a multiple of 2048); ranges [F,tiles,2] u32 = positions in
  *   that compacted list */
 int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, const char* image_buffer, int P, int F,
                       int width, int height, int64_t num_rendered, uint64_t* keys, uint32_t* point_list,

@@ -36,6 +36,8 @@ def load():
         lib.ref_knn.restype = None
         lib.ref_knn.argtypes = [i, p, p]
         lib.ref_sync.restype = i
+        lib.truth_blend_backward.restype = None
+        lib.truth_blend_backward.argtypes = [i, i] + [p] * 8 + [f] + [p] * 7
         _lib = lib
     return _lib
 
@@ -139,3 +141,23 @@ def knn(points):
     lib.ref_knn(pts.shape[0], _ptr(pts), _ptr(out))
     lib.ref_sync()
     return out
+
+
+def truth_blend_backward(fw, bg, W, H, dL_dpix, dL_dpixdepth, z_far=100.0):
+    """Float64 evaluation of the tile-blend backward (oracle/truth_bwd.cu) on the forward state `fw` of a
+    reference run: same blend decisions as the float forward, float64 values and sums. Returns the tuple
+    rn.preprocess_backward takes: (dL_dmean2D [P,2] w.r.t. NDC, dL_dconic [P,3], dL_dopacity [P], dL_dcolor [P,3],
+    dL_ddepth [P]) as float64 CUDA tensors."""
+    lib = load()
+    dev = bg.device
+    P = fw["radii"].shape[0]
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)
+    dmean, dconic, dop, dcol, ddep = z(P, 2), z(P, 3), z(P), z(P, 3), z(P)
+    g, b, im = fw["geom"], fw["binning"], fw["image"]
+    torch.cuda.synchronize(dev)
+    lib.truth_blend_backward(W, H, _ptr(im["ranges"]), _ptr(b["point_list"]), _ptr(g["means2D"]),
+                             _ptr(g["conic_opacity"]), _ptr(g["rgb"]), _ptr(g["depths"]), _ptr(im["n_contrib"]),
+                             _ptr(bg), z_far, _ptr(dL_dpix), _ptr(dL_dpixdepth), _ptr(dmean), _ptr(dconic),
+                             _ptr(dop), _ptr(dcol), _ptr(ddep))
+    lib.ref_sync()
+    return dmean, dconic, dop, dcol, ddep
