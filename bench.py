@@ -8,6 +8,10 @@ renders, their mean, L1 loss against a ground-truth image, and the complete back
 Gaussian parameters and the control points.  N > 1 (torchrun, one rank per GPU): every rank renders a
 different blurry view over the same replicated Gaussians (views of a batch are sharded across GPUs,
 weak scaling) and the Gaussian gradients are summed with one NCCL all-reduce inside the timed region.
+The step is replayed as ONE CUDA graph (deblurgs_b200.graph.BlurryViewGraph; --no-graph launches it kernel by
+kernel).  The same line also carries BASELINE.json's other multi-GPU shapes, measured in the same run
+("other_configs"): c3 with the SUB-FRAMES of one view sharded across the ranks (strong scaling, the partial blurry
+images summed by an NCCL all-reduce) and c4 with one view per rank (weak).
 
 `--impl reference` times the reference's own implementation on the same GPU: its unmodified CUDA
 extension from baseline/_ref driven by the reference's per-sub-frame Python loop (restated in
@@ -142,12 +146,30 @@ def flat_grad_views(params):
     return flat
 
 
-def make_step_ours(w, world, lambda_t_smooth=0.0):
+def make_step_ours(w, world, lambda_t_smooth=0.0, use_graph=False):
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     gparams = g.parameters()
     cparams = cmm.parameters()
     flat = flat_grad_views(gparams) if world > 1 else None
+
+    if use_graph:
+        from deblurgs_b200.graph import BlurryViewGraph
+        graph = BlurryViewGraph(cmm, 0, w["bg"], (3, w["H"], w["W"]), lambda_t_smooth,
+                                pre_backward=(flat.zero_ if flat is not None else None),
+                                caller_owned_grads=(gparams if flat is not None else ()))
+
+        def step(gt, gt_ready=None):
+            if gt_ready is not None:   # ground truth uploaded on a side stream
+                torch.cuda.current_stream().wait_event(gt_ready)
+            graph.gt.copy_(gt, non_blocking=True)
+            loss = graph.replay()
+            if flat is not None:
+                import torch.distributed as dist
+                dist.all_reduce(flat)
+            return loss
+        step.graph = graph
+        return step
 
     def step(gt, gt_ready=None):
         if flat is not None:
@@ -167,6 +189,30 @@ def make_step_ours(w, world, lambda_t_smooth=0.0):
             import torch.distributed as dist
             dist.all_reduce(flat)
         return loss
+    step.graph = None
+    return step
+
+
+def make_step_subframe_sharded(w, world):
+    """One blurry view, its sub-frames sharded over the ranks (deblurgs_b200.dist.render_blurry_sharded): partial
+    blurred images summed by an all-reduce, every rank evaluates the same L1 loss, Gaussian and trajectory
+    gradients summed by an all-reduce of one flat buffer."""
+    from deblurgs_b200 import dist as dd
+    from deblurgs_b200.loss import blur_photometric_loss
+    cmm, g = w["cmm"], w["gaussians"]
+    params = g.parameters() + cmm.parameters()
+    flat = flat_grad_views(params)
+
+    def step(gt, gt_ready=None):
+        flat.zero_()
+        blurred, pkg, _ = dd.render_blurry_sharded(cmm, 0, w["bg"])
+        loss = blur_photometric_loss(blurred, pkg["render"], gt, 0.0)
+        loss.backward()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat)
+        return loss
+    step.graph = None
     return step
 
 
@@ -234,24 +280,40 @@ def workload_stats(w):
 
 
 def algorithmic_bytes(w, st, sort_bits):
-    """SURVEY.md 8(d) HBM byte model per blurry view, split per stage."""
+    """SURVEY.md 8(d) HBM byte model per blurry view, split per stage (the REFERENCE's algorithm: one 64-bit sort
+    of D duplicates, 12-B pairs, one 8-bit pass per 8 key bits)."""
     P, F, W, H = w["P"], w["F"], w["W"], w["H"]
     M = w["scene"].shs.shape[1]
     G = 44 + 12 * M
     V, D = st["V"], st["D"]
     passes = math.ceil(sort_bits / 8)
+    binning = 2 * 4 * P * F + (V * 16 + D * 12) + D * 12 * 2 * passes + D * 8   # scan + duplicate + sort + ranges
     return {
         "preprocess_fwd": P * G + V * 48,
-        "scan": 2 * 4 * P * F,
-        "duplicate": V * 16 + D * 12,
-        "sort": D * 12 * 2 * passes,
-        "tile_ranges": D * 8,
+        "binning": binning,
         "render_fwd": D * (4 + 44) + F * H * W * (16 + 8),
         "blur_mean": F * H * W * 12 + H * W * 12,
         "bwd_memset": V * 40,
         "render_bwd": D * (4 + 44) + F * H * W * (16 + 8) + V * 40,
         "preprocess_bwd": P * G + P * G + V * 40 + V * 48,
     }
+
+
+def moved_bytes_binning(w, st, tile_key_bits):
+    """Bytes THIS library's binning moves per blurry view (dgs_binning.cu): 4 depth-sort passes over the N entries
+    (4-B keys read twice, 4-B values, 8 B written), the entry scan (8-B rectangle gather, 4 + 8 + 4 B written, 4 B
+    read), and the tile sort (pass 1 generates its items and writes 8 B per duplicate; every later pass reads the
+    4-B keys twice and the values once; the last pass writes only the 4-B Gaussian index)."""
+    N, D = w["P"] * w["F"], st["D"]
+    passes = max(1, math.ceil(tile_key_bits / 8))
+    depth_sort = N * (4 + 8 + 8) * 4 - N * 4          # first pass has no value input
+    scan = N * (4 + 8 + 4 + 8 + 4 + 4)
+    gen_reads = 2 * N * 12                            # offsets + packed rectangles, read by the pass-1 up- and downsweep
+    if passes == 1:
+        tile = gen_reads + D * 4
+    else:
+        tile = gen_reads + D * 8 + (passes - 2) * D * (4 + 8 + 8) + D * (4 + 8 + 4)
+    return depth_sort + scan + tile
 
 
 def read_profile(lib):
@@ -264,33 +326,86 @@ def read_profile(lib):
     return {lib.dgs_profile_stage_name(i).decode(): (ms[i], calls[i]) for i in range(n)}
 
 
-def cpu_baseline(config_name, seconds_budget=25.0):
-    """The numpy oracle (test infrastructure, the checker) timed on one host core on a bounded sample of
-    the same workload: whole sub-frames of the benchmark scene, forward + backward, until the budget is
-    spent (at least one)."""
-    import numpy as np
+def cpu_baseline(bench_config):
+    """PyTorch-CPU evaluation of the same path (oracle/raster_torch_cpu.py: test infrastructure, the checker) on all
+    host cores: pose chain -> projection -> tile keys -> sort -> front-to-back composite -> mean -> L1 -> autograd
+    backward.  Two bounded samples: (1) BASELINE.json's CPU-runnable config c1 in full (one whole blurry view,
+    50 k Gaussians, 256x256, F=4); (2) ONE sub-frame of the benchmark's own workload, scaled to views/s by 1/F."""
     from deblurgs_b200 import synthetic
-    from oracle import pose_torch as pt, raster_np as rn
-    P, W, H, F, order = synthetic.get_config(config_name)
-    cam = synthetic.make_camera(W, H)
-    scene = synthetic.make_scene(P, cam, seed=0)
-    traj = synthetic.make_trajectory(F, order, seed=1)
-    bg = synthetic.make_background().numpy()
-    poses = pt.trajectory(traj.ctrl_trans, traj.ctrl_rot, traj.nu, cam.projection_matrix_t())
-    rng = np.random.default_rng(0)
-    dpix = rng.standard_normal((3, H, W)) / (3 * H * W * F)
-    ddep = np.zeros((1, H, W))
-    a = [t.numpy() for t in (scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs)]
-    done, t0 = 0, time.perf_counter()
-    while done < F and (done == 0 or time.perf_counter() - t0 < seconds_budget):
-        v, p, c = (t.detach().numpy() for t in poses[done])
-        fw = rn.forward(a[0], a[1], a[2], a[3], a[4], 3, v, p, c, bg, W, H, cam.tanfovx, cam.tanfovy)
-        rn.backward(fw, a[0], a[1], a[2], a[4], 3, v, p, c, bg, W, H, cam.tanfovx, cam.tanfovy, dpix, ddep)
-        done += 1
-    dt = time.perf_counter() - t0
-    return {"value": 1.0 / (dt / done * F), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d of %d sub-frames of %s (fwd+bwd, numpy oracle, 1 thread) in %.1f s; "
-                      "views/s extrapolated to F=%d; host has %d cores" % (done, F, config_name, dt, F, os.cpu_count())}
+    from oracle import pose_torch as pt, raster_torch_cpu as rt
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def setup(name):
+        P, W, H, F, order = synthetic.get_config(name)
+        cam = synthetic.make_camera(W, H)
+        sc = synthetic.make_scene(P, cam, seed=0)
+        tr = synthetic.make_trajectory(F, order, seed=1)
+        params = [t.clone() for t in (sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)]
+        return P, W, H, F, cam, tr, params, synthetic.make_background(), synthetic.make_target(cam, seed=2)
+
+    # warm-up (thread pools, allocator) on the tiny config
+    P, W, H, F, cam, tr, params, bg, gt = setup("tiny")
+    rt.blurry_view_step(params, tr.ctrl_trans.clone(), tr.ctrl_rot.clone(), tr.nu, cam.projection_matrix_t(), bg, gt,
+                        W, H, cam.tanfovx, cam.tanfovy)
+    # (1) full c1 view
+    P, W, H, F, cam, tr, params, bg, gt = setup("c1")
+    t0 = time.perf_counter()
+    rt.blurry_view_step(params, tr.ctrl_trans.clone(), tr.ctrl_rot.clone(), tr.nu, cam.projection_matrix_t(), bg, gt,
+                        W, H, cam.tanfovx, cam.tanfovy)
+    t_c1 = time.perf_counter() - t0
+    # (2) one sub-frame of the benchmark workload, forward + backward
+    P, W, H, F, cam, tr, params, bg, gt = setup(bench_config)
+    for t in params:
+        t.requires_grad_(True)
+    v, p, c = pt.trajectory(tr.ctrl_trans, tr.ctrl_rot, tr.nu, cam.projection_matrix_t())[0]
+    t0 = time.perf_counter()
+    img = rt.render_view(*params, 3, v.float(), p.float(), c.float(), bg, W, H, cam.tanfovx, cam.tanfovy)[0]
+    ((img - gt).abs().mean() / F).backward()
+    t_sub = time.perf_counter() - t0
+    return {"value": 1.0 / (t_sub * F), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "PyTorch-CPU (autograd, %d threads): one of the %d sub-frames of %s, forward + backward, in "
+                      "%.1f s; views/s = 1 / (F x that)" % (cores, F, bench_config, t_sub),
+            "c1_full": {"value": 1.0 / t_c1, "unit": UNIT,
+                        "sample": "one whole c1 blurry view (50 k Gaussians, 256x256, F=4, cubic Bezier), forward + "
+                                  "backward incl. the pose chain, in %.1f s" % t_c1}}
+
+
+def time_steps(step, gt_dev, steps, world, device):
+    """`steps` steps between two CUDA events on the current stream; ms per step, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    e0.record()
+    for _ in range(steps):
+        step(gt_dev)
+    e1.record()
+    barrier(world)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def other_config(name, rank, world, device, steps=3, warmup=3):
+    """BASELINE.json configs 3 and 4 in the same run: c3 = one 1080p view, its sub-frames sharded over the ranks (strong
+    scaling: value = views/s of that one view); c4 = one 3 M-Gaussian view per rank (weak: value = world x views/s)."""
+    strong = name == "c3"
+    w = build_workload(name, 0 if strong else rank, device)
+    step = make_step_subframe_sharded(w, world) if (strong and world > 1) else make_step_ours(w, 1 if strong else world)
+    gt = w["gt_host"].to(device)
+    for _ in range(warmup):
+        step(gt)
+    ms = time_steps(step, gt, steps, world, device)
+    loss = float(step(gt).item())
+    P, W, H, F = w["P"], w["W"], w["H"], w["F"]
+    del w, step
+    torch.cuda.empty_cache()
+    return {"workload": "%s: %d Gaussians, %dx%d, num_subframes=%d" % (name, P, W, H, F),
+            "parallelism": ("subframes-sharded-%d (NCCL all-reduce of the blurred image + gradients)" % world) if strong
+            else "views-dp%d" % world,
+            "scaling": "strong" if strong else "weak", "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "value": (1.0 if strong else world) * 1000.0 / ms, "unit": UNIT, "loss_last": loss}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -304,8 +419,12 @@ def main():
     ap.add_argument("--loss", default="l1", choices=["l1", "smooth"],
                     help="l1: mean|blur - gt| (headline); smooth: + 1e-3 * temporal smoothness of the sub-frames "
                          "(SURVEY 8d's second variant: non-uniform per-sub-frame gradients)")
+    ap.add_argument("--split", default="views", choices=["views", "subframes"],
+                    help="N > 1: views = one view per rank (weak scaling, headline); subframes = ONE view, its "
+                         "sub-frames sharded over the ranks (strong scaling)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the c3 / c4 lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -314,14 +433,16 @@ def main():
         return   # the reference is single-GPU: rank 0 alone runs it
     device = torch.device("cuda", local)
     eff_world = 1 if args.impl == "reference" else world
-    w = build_workload(args.config, rank, device)
+    sharded = args.impl == "ours" and args.split == "subframes" and eff_world > 1
+    w = build_workload(args.config, 0 if sharded else rank, device)
     F = w["F"]
     lam = 1e-3 if args.loss == "smooth" else 0.0
+    use_graph = args.impl == "ours" and not args.no_graph and not sharded
 
     if args.impl == "ours":
         from deblurgs_b200 import _lib
         lib = _lib.load()
-        step = make_step_ours(w, eff_world, lam)
+        step = make_step_subframe_sharded(w, eff_world) if sharded else make_step_ours(w, eff_world, lam, use_graph)
     else:
         lib = None
         if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "diff_gaussian_rasterization")):
@@ -336,33 +457,20 @@ def main():
 
     # ---- device-resident timing: inputs already in HBM, CUDA events, max over ranks
     if lib is not None:
-        lib.dgs_profile_read(None, None, 0, 1)
         lib.dgs_launch_count(1)
-        lib.dgs_profile_enable(1)
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(eff_world)
-    e0.record()
-    for _ in range(args.steps):
-        step(gt_dev)
-    e1.record()
-    barrier(eff_world)
+    ms_step = time_steps(step, gt_dev, args.steps, eff_world, device)
     sampler.stop_flag = True
     sampler.join()
-    ms_total = e0.elapsed_time(e1)
     launches = None
-    prof = None
     if lib is not None:
         launches = int(lib.dgs_launch_count(0))
-        prof = read_profile(lib)
-        lib.dgs_profile_enable(0)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if eff_world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = eff_world * 1000.0 / ms_step
+        if step.graph is not None:     # kernels inside a replayed graph are not seen by the launch counter
+            step.graph.check()
+            launches += step.graph.launches_per_replay * args.steps
+    views_per_step = 1 if sharded else eff_world
+    value = views_per_step * 1000.0 / ms_step
 
     # ---- end to end through the public API: pinned-host ground truth in, loss scalar out, every step
     # (the upload runs on a side stream into one of two preallocated device buffers, as a data loader's
@@ -380,6 +488,8 @@ def main():
             gt_ready = copy_stream.record_event()
         loss = step(gt, gt_ready)
         loss_host = loss.item()
+        if getattr(step, "graph", None) is not None and step.graph.check():   # capacity exceeded: re-captured + replayed
+            loss_host = step.graph.loss.item()
         t_now = time.perf_counter()
         step_wall.append((t_now - t_prev) * 1e3)
         t_prev = t_now
@@ -388,7 +498,37 @@ def main():
     if eff_world > 1:
         import torch.distributed as dist
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = eff_world * args.steps / float(t_e2e.item())
+    e2e_value = views_per_step * args.steps / float(t_e2e.item())
+
+    # ---- per-stage CUDA-event times: a separate pass, kernel by kernel (events inside a replayed graph cannot be read)
+    prof = None
+    if lib is not None and not sharded:
+        eager = make_step_ours(w, 1, lam, False) if use_graph else step
+        if use_graph:
+            for p in w["gaussians"].parameters():
+                p.grad = None
+        for _ in range(2):
+            eager(gt_dev)
+        torch.cuda.synchronize()
+        lib.dgs_profile_read(None, None, 0, 1)
+        lib.dgs_profile_enable(1)
+        n_prof = 5
+        for _ in range(n_prof):
+            eager(gt_dev)
+        torch.cuda.synchronize()
+        prof = read_profile(lib)
+        lib.dgs_profile_enable(0)
+
+    # ---- BASELINE.json's other shapes (c3 sub-frame split, c4 view batch) in the same run
+    others = None
+    if args.impl == "ours" and not args.no_other_configs and args.config == "c2" and not sharded:
+        others = {}
+        for name in ("c3", "c4"):
+            try:
+                others[name] = other_config(name, rank, eff_world, device)
+            except Exception as e:   # never lose the headline line to an out-of-memory on the big shapes
+                others[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.empty_cache()
 
     if eff_world > 1:
         import torch.distributed as dist
@@ -397,23 +537,32 @@ def main():
     if rank != 0:
         return
     clocks = sampler.summary()
+    if sharded:
+        par, scaling = "subframes-sharded-%d" % eff_world, "strong"
+    else:
+        par, scaling = "views-dp%d" % eff_world, "weak"
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": eff_world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_subframe": ms_step / F,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %d Gaussians, %dx%d, num_subframes=%d, SH degree 3, se3 Bezier order %d, "
-                               "one blurry view per GPU per step (fwd+bwd, %s), inputs larger than L2"
-                               % (args.config, w["P"], w["W"], w["H"], F, w["order"],
+                               "one blurry view per %s per step (fwd+bwd, %s), inputs larger than L2"
+                               % (args.config, w["P"], w["W"], w["H"], F, w["order"], "job" if sharded else "GPU",
                                   "L1 loss" if lam == 0.0 else "L1 + 1e-3 temporal-smoothness loss"),
-                   "parallelism": "views-dp%d" % eff_world, "loss_last": loss_host},
+                   "parallelism": par},
+        "loss_last": loss_host,
+        "launch_mode": "cuda-graph replay (one launch per step)" if use_graph else "kernel by kernel",
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["gt_host"].numel() * 4),
-                "d2h_bytes_per_step": 4,
+                "d2h_bytes_per_step": 4 + (24 if use_graph else 0),
                 "ms_per_step_min_median_max": [round(min(step_wall), 3), round(statistics.median(step_wall), 3),
                                                round(max(step_wall), 3)]},
     }
+    if others:
+        out["other_configs"] = others
     if args.impl == "reference":
         out["impl"] = "reference"
+        out["launch_mode"] = "kernel by kernel (the reference synchronises once per sub-frame)"
         out["reference_kind"] = ("reference CUDA extension (baseline/_ref, unmodified, sm_100 build) on the same "
                                  "B200, driven by the reference's per-sub-frame loop")
         out["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
@@ -424,51 +573,66 @@ def main():
         return
 
     out["gpu_launches"] = launches
+    if prof is None:      # sub-frame-sharded run: no per-stage breakdown
+        print(json.dumps(out))
+        return
     st = workload_stats(w)
     tb, sb = C.c_int(0), C.c_int(0)
     lib.dgs_key_bits(w["W"], w["H"], F, C.byref(tb), C.byref(sb))
-    abytes = algorithmic_bytes(w, st, 32 + tb.value + sb.value)
-    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
-    out["stage_ms_per_step"] = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1] > 0}
+    abytes = algorithmic_bytes(w, st, 32 + tb.value)       # the reference sorts [tile | depth] per sub-frame
+    stage_ms = {k: (v[0] / n_prof) for k, v in prof.items() if v[1] > 0}          # ms per step
+    stage_ms["binning"] = sum(stage_ms.get(k, 0.0) for k in ("depth_sort", "scan", "tile_sort"))
+    out["stage_ms_per_step"] = {k: round(v, 4) for k, v in stage_ms.items()}
+    out["stage_ms_note"] = "CUDA events around every stage in a separate kernel-by-kernel pass (5 steps)"
     out["workload_stats"] = st
-    sm_mhz = clocks["sm_mhz"] or 1965.0
+    # FP32 FMA rate of this GPU, measured (register-resident FMA kernel) right here
+    pk, mhz = C.c_double(0.0), C.c_double(0.0)
+    _lib.check(lib.dgs_measure_fp32_peak(C.byref(pk), C.byref(mhz), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "dgs_measure_fp32_peak")
+    fp32_peak = pk.value
     n_sm = torch.cuda.get_device_properties(device).multi_processor_count
-    fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
     flops = {"render_fwd": 14 * st["E"] + 18 * st["K"], "render_bwd": 16 * st["E_b"] + 88 * st["K"]}
-    # dominant kernel among the stages with an algorithmic work figure (under a profiler the tiny latency-bound
-    # stages can show the largest event times)
+    # dominant kernel among the stages with an algorithmic work figure
     dom = max((k for k in stage_ms if k in flops or k in abytes), key=stage_ms.get)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.config, {}).get(dom)
+    hbm, src = measured_peaks()
     if dom in flops:
         ach = flops[dom] / (stage_ms[dom] * 1e-3) / 1e12
         out["roofline"] = {"kernel": dom, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                            "frac": ach / fp32_peak, "traffic": traffic,
-                           "peak_source": "derived: %d SMs x 128 lanes x 2 x %.0f MHz (SM clock sampled during the "
-                                          "timed region); MEASURED_PEAKS.json has no fp32 entry" % (n_sm, sm_mhz),
+                           "peak_source": "measured in this run: FP32 FMA kernel, best of 6 (implies %.0f MHz x %d SMs x 128 "
+                                          "lanes x 2; the SM clock sampled during the timed region was %s MHz)"
+                                          % (mhz.value, n_sm, clocks["sm_mhz"]),
                            "algorithmic_flops_per_launch": flops[dom], "ms_per_launch": stage_ms[dom]}
         if traffic:   # why the bound is not HBM: measured DRAM traffic of the same kernel against the copy bandwidth
-            hbm_pk, _ = measured_peaks()
             out["roofline"]["dram_gbs"] = traffic / (stage_ms[dom] * 1e-3) / 1e9
-            out["roofline"]["dram_frac_of_hbm_peak"] = out["roofline"]["dram_gbs"] / hbm_pk
+            out["roofline"]["dram_frac_of_hbm_peak"] = out["roofline"]["dram_gbs"] / hbm
     else:
-        hbm, src = measured_peaks()
         ach = abytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
         out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                            "frac": ach / hbm, "traffic": traffic, "peak_source": src,
                            "algorithmic_bytes_per_launch": abytes[dom], "ms_per_launch": stage_ms[dom]}
-    hbm, src = measured_peaks()
-    hbm_stages = ["preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges", "bwd_memset", "preprocess_bwd"]
+    # the HBM-bound stages: SURVEY 8(d)'s algorithmic bytes (the reference's algorithm) next to the bytes this
+    # library's own binning actually moves
+    hbm_stages = ["preprocess_fwd", "binning", "bwd_memset", "preprocess_bwd"]
     hb = sum(abytes[k] for k in hbm_stages if k in stage_ms)
     ht = sum(stage_ms[k] for k in hbm_stages if k in stage_ms)
-    out["roofline_hbm_group"] = {"kernels": hbm_stages, "bound": "hbm", "achieved": hb / (ht * 1e-3) / 1e9,
-                                 "peak": hbm, "unit": "GB/s", "frac": hb / (ht * 1e-3) / 1e9 / hbm,
-                                 "peak_source": src, "algorithmic_bytes": hb, "ms": ht}
+    moved = moved_bytes_binning(w, st, max(1, (w["cam"].width + 15) // 16 * ((w["cam"].height + 15) // 16) - 1).bit_length())
+    out["roofline_hbm_group"] = {
+        "kernels": hbm_stages, "bound": "hbm", "achieved": hb / (ht * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+        "frac": hb / (ht * 1e-3) / 1e9 / hbm, "peak_source": src, "algorithmic_bytes": hb, "ms": ht,
+        "binning": {"ms": stage_ms["binning"], "algorithmic_bytes": abytes["binning"],
+                    "algorithmic_gbs": abytes["binning"] / (stage_ms["binning"] * 1e-3) / 1e9,
+                    "moved_bytes": moved, "moved_gbs": moved / (stage_ms["binning"] * 1e-3) / 1e9,
+                    "moved_frac_of_hbm_peak": moved / (stage_ms["binning"] * 1e-3) / 1e9 / hbm,
+                    "note": "algorithmic = the reference's scan + duplicateWithKeys + one 64-bit sort of 12-B pairs + "
+                            "identifyTileRanges (SURVEY 8d); moved = what dgs_binning.cu reads and writes"}}
     if not args.no_cpu_baseline and eff_world == 1:
-        out["cpu_baseline"] = cpu_baseline(args.config, args.cpu_budget)
+        out["cpu_baseline"] = cpu_baseline(args.config)
     print(json.dumps(out))
 
 

@@ -34,6 +34,7 @@ SIGNATURES = {
                                    _i, _i, _i, _i] + _FWD_COMMON +
                               [_i, _i, _p, _p, _p, _p, _f, _i64, C.POINTER(_i64), _p]),
     "dgs_blur_forward_status": (_i, [_p, _i, _i, C.POINTER(_i64), C.POINTER(_i), _p]),
+    "dgs_blur_forward_status_offset": (C.c_size_t, [_i, _i]),
     "dgs_blur_backward_scratch_bytes": (C.c_size_t, [_i, _i]),
     "dgs_blur_backward": (_i, [_i, _i, _i, _i, _i64] + _FWD_COMMON +
                           [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p] + [_p] * 11 + [_p]),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "dgs_debug_image": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "dgs_debug_sort_scratch_bytes": (C.c_size_t, [_i, _i64]),
     "dgs_debug_sort": (_i, [_i, _i64, _i, _p, _p, _p, _p, _p]),
+    "dgs_measure_fp32_peak": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), _p]),
     "dgs_profile_enable": (_i, [_i]),
     "dgs_profile_num_stages": (_i, []),
     "dgs_profile_stage_name": (C.c_char_p, [_i]),

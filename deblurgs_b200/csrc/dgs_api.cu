@@ -451,6 +451,11 @@ int dgs_blur_forward_hint(
                              blur_denominator, binning_capacity, num_rendered, stream);
 }
 
+size_t dgs_blur_forward_status_offset(int P, int F)
+{
+    return geom_layout((size_t)(P > 0 ? P : 0), (size_t)(F > 0 ? F : 0)).status;
+}
+
 int dgs_blur_forward_status(const char* geom_buffer, int P, int F, int64_t* num_rendered, int* overflow, void* stream)
 {
     if (num_rendered) *num_rendered = 0;
@@ -772,6 +777,56 @@ int dgs_debug_sort(int nseg, int64_t len, int key_bits, const uint32_t* keys, ui
     const size_t n = (size_t)nseg * len;
     k_debug_unpad<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nseg, (uint32_t)len, (uint32_t)stride, kb, vb, keys_sorted, index_sorted);
     DGS_CUDA(cudaGetLastError(), "dgs_debug_sort");
+    return DGS_OK;
+}
+
+// ---- FP32 FMA throughput of this GPU (denominator of the blend kernels' roofline) -------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float* sink, int iters, float a, float b)
+{
+    // 16 independent FMA chains per thread: enough ILP to fill the FP32 pipes from 8 warps per scheduler
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], a, b);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc += v[i];
+    if (acc == 123.456f) sink[0] = acc;   // never true: keeps the chains alive
+}
+
+int dgs_measure_fp32_peak(double* tflops, double* sm_clock_mhz_hint, void* stream)
+{
+    if (!tflops) return fail(DGS_ERR_INVALID_ARGUMENT, "dgs_measure_fp32_peak: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    DGS_CUDA(cudaGetDevice(&dev), "get device");
+    DGS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+    float* sink = nullptr;
+    DGS_CUDA(cudaMalloc(&sink, sizeof(float)), "fp32 peak sink");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {         // first repetitions warm the clocks up
+        cudaEventRecord(e0, st);
+        k_fma_peak<<<blocks, 256, 0, st>>>(sink, iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+        if (ms > 0.f && flops / (ms * 1e-3) / 1e12 > best) best = flops / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    DGS_CUDA(cudaGetLastError(), "fp32 peak");
+    *tflops = best;
+    if (sm_clock_mhz_hint) *sm_clock_mhz_hint = best * 1e12 / (2.0 * 128.0 * sms) / 1e6;   // clock this rate implies
     return DGS_OK;
 }
 

@@ -73,6 +73,10 @@ def _require_cuda(t, name):
 _CAPACITY_HINT = {}
 _KEEP_SCRATCH = False
 _last_scratch = None
+# Fully asynchronous mode (CUDA-graph capture, graph.BlurryViewGraph): a fixed binning capacity, nothing is waited
+# for, num_rendered stays on the device; the geometry buffers of the calls made in this mode are collected so that
+# the owner can read their status records.
+_ASYNC = None   # None, or {"capacity": int, "geoms": [(tensor, P, F), ...]}
 
 
 def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
@@ -102,6 +106,8 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
         return color, depth, radii, blur, 0, geom.t, binning.t, img.t
     shape_key = (dev.index, P, F, H, W)
     hint = 0 if (exact or os.environ.get("DGS_EXACT_BINNING") == "1") else _CAPACITY_HINT.get(shape_key, 0)
+    if _ASYNC is not None:
+        hint = int(_ASYNC["capacity"])
     with torch.cuda.device(dev):
         rc = lib.dgs_blur_forward_hint(
             geom.cb, None, binning.cb, None, img.cb, None,
@@ -115,12 +121,15 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
             int(bool(prefiltered)), int(bool(use_sigmoid)),
             _lib.ptr(color), _lib.ptr(depth), _lib.ptr(radii),
             _lib.ptr(blur), float(blur_denominator),
-            int(hint), C.byref(num_rendered), _stream_ptr(dev))
+            int(hint), None if _ASYNC is not None else C.byref(num_rendered), _stream_ptr(dev))
     # drop the ctypes callbacks: they close over the _Buffer objects (a reference cycle), and a cycle
     # would keep hundreds of MB of state buffers alive until Python's cyclic GC runs, forcing the caching
     # allocator to cudaMalloc fresh blocks every step in the meantime
     geom.cb = binning.cb = img.cb = None
     _lib.check(rc, "dgs_blur_forward_hint")
+    if _ASYNC is not None:
+        _ASYNC["geoms"].append((geom.t, P, F))
+        return color, depth, radii, blur, -1, geom.t, binning.t, img.t    # -1: number of duplicates unknown on the host
     D = int(num_rendered.value)
     _CAPACITY_HINT[shape_key] = D + D // 4 + 65536
     return color, depth, radii, blur, D, geom.t, binning.t, img.t

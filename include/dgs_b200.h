@@ -117,6 +117,10 @@ int dgs_blur_forward_hint(
 /* D and the overflow flag of a forward call, read from its geometry buffer (synchronises the stream). */
 int dgs_blur_forward_status(const char* geom_buffer, int P, int F, int64_t* num_rendered, int* overflow,
                             void* stream);
+/* Byte offset, from the 128-B aligned start of the geometry buffer, of the 24-byte status record
+ * { uint64 num_rendered; uint64 padded; uint32 overflow; uint32 n_chunks } -- for callers that copy it themselves
+ * (e.g. as a memcpy node of a captured CUDA graph). */
+size_t dgs_blur_forward_status_offset(int P, int F);
 
 /*
  * Batched backward.  dL_dpix [F,3,H,W], dL_dpixdepth [F,1,H,W] (either may be NULL = zeros);
@@ -225,6 +229,10 @@ int dgs_key_bits(int width, int height, int F, int* tile_bits, int* subframe_bit
  * dgs_debug_workload replays the compositing loop and writes {E, K, E_b} (list entries
  * evaluated, entries that contributed, entries replayed by the backward) to out_dev[3] (device).
  */
+/* Measured FP32 FMA throughput of the current device in TFLOP/s (a register-resident FMA kernel, best of 6 short
+ * runs; ~10 ms): the denominator of the issue-bound blend kernels' roofline.  implied_sm_mhz (optional) = the SM
+ * clock that rate corresponds to at 128 FMA lanes per SM. */
+int dgs_measure_fp32_peak(double* tflops, double* implied_sm_mhz, void* stream);
 int dgs_profile_enable(int on);
 int dgs_profile_num_stages(void);
 const char* dgs_profile_stage_name(int i);

@@ -21,13 +21,17 @@ class _Shs:
 def test_algorithmic_byte_model_covers_every_hbm_stage():
     w = {"P": 300000, "F": 16, "W": 600, "H": 400, "scene": type("S", (), {"shs": _Shs})}
     st = {"V": 4339284, "D": 19154524, "E": 1777802608, "K": 252057426, "E_b": 1751127673}
-    ab = bench.algorithmic_bytes(w, st, 46)
-    for k in ["preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges", "bwd_memset", "preprocess_bwd",
-              "render_fwd", "render_bwd", "blur_mean"]:
+    ab = bench.algorithmic_bytes(w, st, 42)
+    for k in ["preprocess_fwd", "binning", "bwd_memset", "preprocess_bwd", "render_fwd", "render_bwd", "blur_mean"]:
         assert ab[k] > 0
     G = 44 + 12 * 16
     assert ab["preprocess_fwd"] == 300000 * G + st["V"] * 48
-    assert ab["sort"] == st["D"] * 12 * 2 * 6            # the reference's single 46-bit sort: 6 passes of 12-B pairs
+    # binning = scan + duplicate + the reference's single 42-bit sort (6 passes of 12-B pairs) + ranges
+    assert ab["binning"] == 8 * 300000 * 16 + (st["V"] * 16 + st["D"] * 12) + st["D"] * 12 * 2 * 6 + st["D"] * 8
+    # what this library's binning moves is far less than that, and is reported next to it
+    moved = bench.moved_bytes_binning(w, st, 10)
+    assert 0 < moved < 0.5 * ab["binning"]
+    assert bench.moved_bytes_binning(w, st, 8) < moved < bench.moved_bytes_binning(w, st, 17)
 
 
 def test_peaks_and_clock_sampler_degrade_gracefully():
@@ -51,5 +55,5 @@ def test_workload_table_matches_baseline_configs():
 def test_bench_cli_declares_the_contract_flags():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
     assert r.returncode == 0
-    for flag in ["--gpus", "--steps", "--warmup", "--impl", "--config", "--loss"]:
+    for flag in ["--gpus", "--steps", "--warmup", "--impl", "--config", "--loss", "--split", "--no-graph"]:
         assert flag in r.stdout
