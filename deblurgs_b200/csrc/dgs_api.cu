@@ -129,8 +129,9 @@ BinLayout bin_layout(size_t capacity, size_t F, size_t tiles)
     L.capacity = C;
     L.passes = sort_pass_plan(bits_for((uint32_t)(tiles > 1 ? tiles : 1)), &L.bits);
     const size_t chunks = C / SORT_CHUNK;
-    size_t o = 0;
+    size_t o = 128;                       // BinHeader
     L.point_list = o; o = align_up(o + C * sizeof(uint32_t));
+    L.wmask = o; o = align_up(o + C);
     L.keys_a = o; if (L.passes >= 2) o = align_up(o + C * sizeof(uint32_t));
     L.vals_a = o; if (L.passes >= 2) o = align_up(o + C * sizeof(uint32_t));
     L.keys_b = o; if (L.passes >= 3) o = align_up(o + C * sizeof(uint32_t));
@@ -215,6 +216,8 @@ static BinState bind_bin_state(char* geom, const GeomLayout& G)
     b.ticket = (uint32_t*)(geom + G.ticket);
     return b;
 }
+
+__global__ void k_write_u64(unsigned long long* dst, unsigned long long v) { *dst = v; }
 
 // Pinned host landing zone of the asynchronous status read-back (one per host thread) and its event.
 struct StatusMailbox {
@@ -355,7 +358,13 @@ static int blur_forward_impl(
         if (!bin) return fail(DGS_ERR_ALLOC, "binning buffer allocation failed");
         bin = aligned128(bin);
         uint32_t* point_list = (uint32_t*)(bin + B.point_list);
+        uint8_t* wmask = (uint8_t*)(bin + B.wmask);
         uint2* chunk_tab = (uint2*)(bin + B.chunk_first);
+        {   // header: where the backward finds the capacity-dependent arrays (a memset node: capture-safe, no host source)
+            static_assert(sizeof(BinHeader) == 8, "header is one 64-bit word");
+            DGS_CUDA(cudaMemsetAsync(bin, 0, 128, st), "header memset");
+            k_write_u64<<<1, 1, 0, st>>>((unsigned long long*)bin, (unsigned long long)B.wmask);
+        }
 
         if (F > 0 && tiles > 0)
             DGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)F * tiles * sizeof(uint2), st), "ranges memset");
@@ -386,7 +395,7 @@ static int blur_forward_impl(
             }
         }
         if (F > 0 && pixels > 0) {
-            { StageTimer t(ST_RENDER_FWD, st, 1); launch_render_fwd(p, ranges, point_list, final_T, n_contrib, out_color, out_depth, st); }
+            { StageTimer t(ST_RENDER_FWD, st, 1); launch_render_fwd(p, ranges, point_list, wmask, final_T, n_contrib, out_color, out_depth, st); }
             if (out_blur) { StageTimer t(ST_BLUR_MEAN, st, 1); launch_blur_mean(out_color, F, 3 * pixels, blur_denominator, out_blur, st); }
         }
         DGS_CUDA(cudaGetLastError(), "forward launch");
@@ -527,7 +536,8 @@ int dgs_blur_backward(
     b.ranges = (const uint2*)(img + I.ranges);
     b.final_T = (const float*)(img + I.final_T);
     b.n_contrib = (const uint32_t*)(img + I.n_contrib);
-    b.point_list = (const uint32_t*)bin;   // point_list is the first array of the binning buffer
+    b.bin_header = (const BinHeader*)bin;
+    b.point_list = (const uint32_t*)(bin + 128);   // point_list follows the 128-B header of the binning buffer
     b.dL_dpix = dL_dpix;
     b.dL_dpixdepth = dL_dpixdepth;
     b.dL_dblur = dL_dblur;
@@ -654,7 +664,7 @@ int dgs_debug_workload(const char* geom_buffer, const char* binning_buffer, cons
     char* bin = aligned128((char*)binning_buffer);
     bind_geom(p, geom, G);
     DGS_CUDA(cudaMemsetAsync(out_dev, 0, 3 * sizeof(uint64_t), st), "workload memset");
-    launch_workload(p, (const uint2*)(img + I.ranges), (const uint32_t*)bin,
+    launch_workload(p, (const uint2*)(img + I.ranges), (const uint32_t*)(bin + 128),
                     (const uint32_t*)(img + I.n_contrib), (unsigned long long*)out_dev, st);
     DGS_CUDA(cudaGetLastError(), "workload");
     return DGS_OK;
@@ -717,7 +727,7 @@ int dgs_debug_binning(const char* geom_buffer, const char* binning_buffer, const
     char* img = aligned128((char*)image_buffer);
     char* bin = aligned128((char*)binning_buffer);
     launch_debug_lists(P, F, (int)tiles, ref_tile_bits((uint32_t)tiles), (const uint2*)(img + I.ranges),
-                       (const uint32_t*)bin, (const float4*)(geom + G.geo0), (const uint32_t*)(geom + G.seg_start),
+                       (const uint32_t*)(bin + 128), (const float4*)(geom + G.geo0), (const uint32_t*)(geom + G.seg_start),
                        (const uint32_t*)(geom + G.seg_adj), keys, point_list, ranges, (cudaStream_t)stream);
     DGS_CUDA(cudaGetLastError(), "debug lists");
     return DGS_OK;

@@ -105,6 +105,7 @@ struct HalvingReduce {
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
 
 struct BwdSmem {
+    uint8_t wm[DGS_TILE_PIX];            // which warps of the tile blended the staged entry (written by the forward)
     uint32_t id[DGS_TILE_PIX];           // Gaussian index of the staged entry
     float2 xy[DGS_TILE_PIX];
     float4 con[DGS_TILE_PIX];
@@ -197,8 +198,15 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
     const float pixfx = (float)pixx, pixfy = (float)pixy;
 
     const uint2 range = decode_range(p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile]);
-    const uint32_t a_xy = smem_addr(sm.xy), a_con = smem_addr(sm.con), a_rgbd = smem_addr(sm.rgbd);
-    const uint32_t a_id = smem_addr(sm.id);
+    // shared-window addresses the compiler cannot rematerialise inside the pair loop (it otherwise rebuilds them from
+    // SR_CgaCtaId on every iteration)
+    uint32_t a_xy, a_con, a_rgbd, a_id;
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_xy) : "r"(smem_addr(sm.xy)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_con) : "r"(smem_addr(sm.con)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_rgbd) : "r"(smem_addr(sm.rgbd)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_id) : "r"(smem_addr(sm.id)));
+    const uint8_t* __restrict__ wmask = reinterpret_cast<const uint8_t*>(p.bin_header) + p.bin_header->wmask_offset;
+    const unsigned wbit = strip * BWD_WARPS + warp;      // this warp's index among the 8 warps of the forward's tile block
 
     const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
     const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
@@ -256,7 +264,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
             const int slot = k * BWD_THREADS + tid;
             const int progress = i * DGS_TILE_PIX + slot;
             if (progress < list_len) {
-                const uint32_t id = p.point_list[range.x + list_len - progress - 1];
+                const uint32_t lp = range.x + list_len - progress - 1;
+                const uint32_t id = p.point_list[lp];
+                sm.wm[slot] = wmask[lp];
                 const float4 a = geo0[id];
                 const float4 c = geo2[id];
                 sm.id[slot] = id;
@@ -271,9 +281,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
         const int first_pos = list_len - i * DGS_TILE_PIX - 1;
         for (int c0 = 0; c0 < batch; c0 += 32) {
             const int jl = c0 + (int)lane;
-            bool keep = false;
-            if (jl < batch && first_pos - jl < warp_max)
-                keep = entry_reaches_rect(sm.xy[jl], sm.con[jl], rx0, ry0, rx1, ry1);
+            // the forward recorded which (warp, entry) pairs blended at least one pixel: visit exactly those
+            const bool keep = jl < batch && ((sm.wm[jl] >> wbit) & 1u);
             unsigned mask = __ballot_sync(FULL_MASK, keep);
             while (mask) {
                 const int j = c0 + __ffs(mask) - 1;
