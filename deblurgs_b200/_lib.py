@@ -58,10 +58,15 @@ SIGNATURES = {
     "dgs_pose_backward": (_i, [_i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_blur_loss_forward": (_i, [_i, _i64, _p, _p, _p, _f, _p, _p, _p]),
     "dgs_blur_loss_backward": (_i, [_i, _i64, _p, _p, _p, _f, _p, _p, _p, _p]),
+    "dgs_tv_loss_forward": (_i, [_i64, _i, _i, _p, _p, _p, _p]),
+    "dgs_tv_loss_backward": (_i, [_i64, _i, _i, _p, _p, _p, _p]),
+    "dgs_hinge_l2_forward": (_i, [_i64, _p, _p, _p, _p]),
+    "dgs_hinge_l2_backward": (_i, [_i64, _p, _p, _p, _p]),
     "dgs_activate_forward": (_i, [_i, _i, _p, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p]),
     "dgs_activate_backward": (_i, [_i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "dgs_adam_step": (_i, [_i, _p, _p, _p, _p, C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(_i64),
                            C.c_double, C.c_double, C.c_double, C.c_double, _p]),
+    "dgs_rows_gather": (_i, [_i, _p, _p, C.POINTER(_i), C.POINTER(_i), _i64, _p, _p, _p]),
     "dgs_mark_visible": (_i, [_i, _p, _p, _p, _p, _p]),
     "dgs_knn_scratch_bytes": (C.c_size_t, [_i]),
     "dgs_knn_mean_dist2": (_i, [_i, _p, _p, _p, _p]),

@@ -179,9 +179,62 @@ __global__ void __launch_bounds__(256) k_adam(const AdamBatch b)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Densify / prune on the SoA parameter store (reference: scene/gaussian_model.py:300-454 -- prune_points,
+// cat_tensors_to_optimizer / densification_postfix, densify_and_clone, densify_and_split).  Every one of those
+// operations is "new row r of EVERY per-Gaussian tensor = old row src[r]" with the Adam moments of appended rows
+// zeroed; the reference runs it as ~40 torch index / cat launches over the 6 parameter tensors, their 12 moment
+// tensors and the 3 statistics vectors.  Here one launch rebuilds all of them: a thread per output float, rows of
+// one tensor contiguous across the block so loads and stores are coalesced along the row.
+// ---------------------------------------------------------------------------------------
+struct GatherTensor { const float* in; float* out; int width; int zero_new; long long first_block; };
+struct GatherBatch { GatherTensor t[DGS_GATHER_MAX_TENSORS]; int count; long long n_out; };
+
+__global__ void __launch_bounds__(256) k_rows_gather(const GatherBatch b, const long long* __restrict__ src,
+                                                     const unsigned char* __restrict__ carry)
+{
+    int ti = 0;
+#pragma unroll 1
+    for (int k = 1; k < b.count; k++)
+        if ((long long)blockIdx.x >= b.t[k].first_block) ti = k;
+    const GatherTensor& t = b.t[ti];
+    const long long i = ((long long)blockIdx.x - t.first_block) * 256 + threadIdx.x;     // output float index
+    if (i >= b.n_out * t.width) return;
+    const long long row = i / t.width;
+    const int c = (int)(i - row * t.width);
+    float v = 0.f;
+    if (!(t.zero_new && carry != nullptr && carry[row] == 0)) v = __ldg(t.in + src[row] * t.width + c);
+    t.out[i] = v;
+}
+
 }  // namespace dgs
 
 extern "C" {
+
+int dgs_rows_gather(int n_tensors, const float* const* in, float* const* out, const int* width, const int* zero_new,
+                    int64_t n_out, const int64_t* src_rows, const uint8_t* carry, void* stream)
+{
+    if (n_tensors < 0 || n_tensors > DGS_GATHER_MAX_TENSORS || n_out < 0)
+        return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_rows_gather: invalid argument");
+    if (n_tensors == 0 || n_out == 0) return DGS_OK;
+    if (!in || !out || !width || !zero_new || !src_rows) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_rows_gather: null argument");
+    dgs::GatherBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n_out = n_out;
+    long long blocks = 0;
+    for (int k = 0; k < n_tensors; k++) {
+        if (width[k] <= 0 || !in[k] || !out[k]) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_rows_gather: bad tensor");
+        dgs::GatherTensor& t = b.t[b.count++];
+        t.in = in[k]; t.out = out[k]; t.width = width[k]; t.zero_new = zero_new[k]; t.first_block = blocks;
+        blocks += ((long long)n_out * width[k] + 255) / 256;
+    }
+    if (blocks > 0x7fffffffLL) return dgs::fail(DGS_ERR_UNSUPPORTED, "dgs_rows_gather: size not supported");
+    {
+        dgs::StageTimer timer(dgs::ST_DENSIFY, (cudaStream_t)stream, 1);
+        dgs::k_rows_gather<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, (const long long*)src_rows, carry);
+    }
+    { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_rows_gather"); }
+}
 
 int dgs_activate_forward(int P, int sh_coeffs, const float* features_dc, const float* features_rest,
                          const float* scaling, const float* rotation, const float* opacity,

@@ -1,6 +1,7 @@
-"""Fused photometric loss of the blurry-view training step (reference: train.py:147-163,
-utils/loss_utils.py:17-18, 80-93): loss = l1_loss(blurred, gt) + lambda_t_smooth *
-batchwise_smoothness_loss(subframes), forward and backward in one kernel each."""
+"""Loss block of the blurry-view training step (reference: train.py:147-163, utils/loss_utils.py):
+`blur_photometric_loss` = l1_loss(blurred, gt) + lambda_t_smooth * batchwise_smoothness_loss(subframes), forward and
+backward in one kernel each; `tv_loss` (depth smoothness) and `hinge_l2` (opacity range penalty), one kernel each way;
+`training_loss` = the reference's weighted sum of the four."""
 import ctypes as C
 
 import torch
@@ -61,3 +62,88 @@ class _BlurLoss(torch.autograd.Function):
 def blur_photometric_loss(blurred, subframes, gt, lambda_t_smooth=0.0):
     """l1_loss(blurred, gt) + lambda_t_smooth * batchwise_smoothness_loss(subframes) as a 0-dim tensor."""
     return _BlurLoss.apply(blurred, subframes, gt, lambda_t_smooth)
+
+
+def _st(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _TV(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.DgsError("tv_loss: CUDA tensor required (libdgs_b200 has no CPU path)")
+        if x.dim() != 4:
+            raise _lib.DgsError("tv_loss: x must be [B,C,H,W]")
+        xc = x.detach().float().contiguous()
+        B, Cc, H, W = xc.shape
+        out = torch.empty(1, dtype=torch.float32, device=xc.device)
+        scratch = torch.empty(2, dtype=torch.float64, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.dgs_tv_loss_forward(B * Cc, H, W, _lib.ptr(xc), _lib.ptr(out), _lib.ptr(scratch), _st(xc)),
+                       "dgs_tv_loss_forward")
+        ctx.save_for_backward(xc)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        (xc,) = ctx.saved_tensors
+        B, Cc, H, W = xc.shape
+        go = grad_out.detach().float().contiguous().reshape(1)
+        dx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.dgs_tv_loss_backward(B * Cc, H, W, _lib.ptr(xc), _lib.ptr(go), _lib.ptr(dx), _st(xc)),
+                       "dgs_tv_loss_backward")
+        return dx
+
+
+class _Hinge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.DgsError("hinge_l2: CUDA tensor required (libdgs_b200 has no CPU path)")
+        xc = x.detach().float().contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=xc.device)
+        scratch = torch.empty(2, dtype=torch.float64, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.dgs_hinge_l2_forward(xc.numel(), _lib.ptr(xc), _lib.ptr(out), _lib.ptr(scratch), _st(xc)),
+                       "dgs_hinge_l2_forward")
+        ctx.save_for_backward(xc)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        (xc,) = ctx.saved_tensors
+        go = grad_out.detach().float().contiguous().reshape(1)
+        dx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.dgs_hinge_l2_backward(xc.numel(), _lib.ptr(xc), _lib.ptr(go), _lib.ptr(dx), _st(xc)),
+                       "dgs_hinge_l2_backward")
+        return dx
+
+
+def tv_loss(x):
+    """utils/loss_utils.py:66-78 on a [B,C,H,W] tensor: l2 of the vertical + l2 of the horizontal neighbour differences."""
+    return _TV.apply(x)
+
+
+def hinge_l2(x):
+    """utils/loss_utils.py:95-104: mean of x^2 where x <= 0 and (x - 1)^2 where x >= 1."""
+    return _Hinge.apply(x)
+
+
+def training_loss(blurred, subframes, gt, depths=None, opacity=None, lambda_t_smooth=0.0, lambda_depth_tv=0.0,
+                  lambda_hinge=0.0):
+    """The reference's loss (train.py:147-163): Ll1 + lambda_t_smooth * L_t_smooth + lambda_depth_tv * L_depth_tv +
+    lambda_hinge * L_hinge, with the reference's gating (a term whose weight is 0 is not evaluated).
+    depths [F,1,H,W] (query()['depths']), opacity = gaussians._opacity."""
+    loss = blur_photometric_loss(blurred, subframes, gt, lambda_t_smooth)
+    if lambda_depth_tv > 0.0:
+        loss = loss + lambda_depth_tv * tv_loss(depths)
+    if lambda_hinge > 0.0:
+        loss = loss + lambda_hinge * hinge_l2(opacity)
+    return loss

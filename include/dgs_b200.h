@@ -278,6 +278,19 @@ int dgs_blur_loss_backward(int F, int64_t chw, const float* subframes, const flo
                            float* dL_dsubframes, void* stream);
 
 /*
+ * The two regularisers of the reference's training loss (train.py:150-163):
+ *   tv_loss  (utils/loss_utils.py:66-78)  x [planes, H, W] (planes = B*C): mean of squared vertical differences +
+ *            mean of squared horizontal differences; the depth smoothness term lambda_depth_tv * tv_loss(depths)
+ *   hinge_l2 (utils/loss_utils.py:95-104) mean of x^2 where x <= 0 and (x-1)^2 where x >= 1; applied to the raw
+ *            opacities (lambda_hinge * hinge_l2(_opacity))
+ * loss_out [1] float, scratch [2] doubles; backward: grad_out = device pointer to dL/dloss (NULL = 1), dL_dx written.
+ */
+int dgs_tv_loss_forward(int64_t planes, int H, int W, const float* x, float* loss_out, double* scratch, void* stream);
+int dgs_tv_loss_backward(int64_t planes, int H, int W, const float* x, const float* grad_out, float* dL_dx, void* stream);
+int dgs_hinge_l2_forward(int64_t n, const float* x, float* loss_out, double* scratch, void* stream);
+int dgs_hinge_l2_backward(int64_t n, const float* x, const float* grad_out, float* dL_dx, void* stream);
+
+/*
  * Gaussian parameter store, the steps either side of the rasterizer.
  *
  * dgs_activate_forward replaces the four getters `render` reads -- get_features (cat of _features_dc
@@ -309,6 +322,19 @@ int dgs_activate_backward(int P, int sh_coeffs, const float* scaling, const floa
 int dgs_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const int64_t* numel, const double* lr, const int64_t* step,
                   double beta1, double beta2, double eps, double clip_grad_value, void* stream);
+
+/*
+ * Densify / prune on the parameter store (reference: scene/gaussian_model.py:300-454: prune_points,
+ * cat_tensors_to_optimizer / densification_postfix, densify_and_clone, densify_and_split): every per-Gaussian
+ * tensor is rebuilt as out[r] = in[src_rows[r]] in ONE launch -- up to DGS_GATHER_MAX_TENSORS tensors (the 6 raw
+ * parameters, their 12 Adam moments, the 3 densification statistics), width[k] floats per row.  Tensors with
+ * zero_new[k] != 0 (the Adam moments) get zeros in the rows where carry[r] == 0 (the appended Gaussians).
+ * HOST arrays of n_tensors entries (device pointers inside); src_rows [n_out] int64 and carry [n_out] uint8 (or NULL
+ * = every row carries) on the device.
+ */
+#define DGS_GATHER_MAX_TENSORS 24
+int dgs_rows_gather(int n_tensors, const float* const* in, float* const* out, const int* width, const int* zero_new,
+                    int64_t n_out, const int64_t* src_rows, const uint8_t* carry, void* stream);
 
 /* present [P] uint8: 1 iff view-space z > 0.2 (reference in_frustum, auxiliary.h:144-169). */
 int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix,

@@ -160,3 +160,104 @@ def test_training_step_through_the_store_reduces_the_loss():
         opt.zero_grad(set_to_none=True)
         losses.append(loss.item())
     assert math.isfinite(losses[-1]) and losses[-1] < losses[0]
+
+
+def test_regularisers_match_the_reference_definitions():
+    """tv_loss / hinge_l2 (utils/loss_utils.py:66-78, 95-104) and the weighted training loss (train.py:147-163)."""
+    from deblurgs_b200.loss import blur_photometric_loss, hinge_l2, training_loss, tv_loss
+    g = torch.Generator().manual_seed(9)
+
+    def ref_tv(x):
+        return ((x[:, :, :-1, :] - x[:, :, 1:, :]) ** 2).mean() + ((x[:, :, :, :-1] - x[:, :, :, 1:]) ** 2).mean()
+
+    def ref_hinge(x):
+        loss = torch.zeros_like(x)
+        loss = torch.where(x <= 0.0, x ** 2, loss)
+        loss = torch.where(x >= 1.0, (x - 1.0) ** 2, loss)
+        return loss.mean()
+
+    for shape in [(5, 1, 37, 53), (2, 3, 16, 16), (1, 1, 2, 2)]:
+        x = (torch.rand(shape, generator=g) * 10).cuda().requires_grad_(True)
+        a, b = tv_loss(x), ref_tv(x)
+        ga, = torch.autograd.grad(a * 1.3, x)
+        gb, = torch.autograd.grad(b * 1.3, x)
+        assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item()) and torch.allclose(ga, gb, rtol=1e-4, atol=1e-7)
+    o = (torch.rand(20_000, 1, generator=g) * 1.4 - 0.2).cuda()
+    o[:5, 0] = torch.tensor([0.0, 1.0, -0.5, 1.5, 0.5])
+    o.requires_grad_(True)
+    a, b = hinge_l2(o), ref_hinge(o)
+    ga, = torch.autograd.grad(a * 0.7, o)
+    gb, = torch.autograd.grad(b * 0.7, o)
+    assert abs(a.item() - b.item()) <= 1e-6 and torch.allclose(ga, gb, rtol=1e-5, atol=1e-10)
+    # the reference's weighted sum
+    F, H, W = 4, 24, 40
+    sub = torch.rand(F, 3, H, W, generator=g).cuda().requires_grad_(True)
+    dep = (torch.rand(F, 1, H, W, generator=g) * 5).cuda().requires_grad_(True)
+    blur = sub.mean(0)
+    gt = torch.rand(3, H, W, generator=g).cuda()
+    mine = training_loss(blur, sub, gt, dep, o, lambda_t_smooth=0.01, lambda_depth_tv=0.1, lambda_hinge=0.1)
+    ref = (blur - gt).abs().mean() + 0.01 * (sub[1:] - sub[:-1]).abs().mean() + 0.1 * ref_tv(dep) + 0.1 * ref_hinge(o)
+    assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    gm = torch.autograd.grad(mine, [sub, dep, o])
+    gr = torch.autograd.grad(ref, [sub, dep, o])
+    for x, y in zip(gm, gr):
+        assert torch.allclose(x, y, rtol=1e-4, atol=1e-9)
+    # a zero weight gates its term off like the reference
+    assert training_loss(blur, sub, gt, None, None, 0.0, 0.0, 0.0).item() == blur_photometric_loss(blur, sub, gt, 0.0).item()
+
+
+def test_fused_densify_rebuild_equals_the_cpu_plan():
+    """One densify_and_prune round on the GPU (one row-gather launch per rebuild, csrc/dgs_params.cu) against the same
+    round executed with torch indexing on CPU tensors, which tests/test_densify.py pins to the reference's semantics
+    (scene/gaussian_model.py:300-454).  The split's random offsets come from different generators on the two
+    devices, so the new positions are compared through the CPU's samples fed to both."""
+    from tests.test_densify import NAMES, ATTR, _store
+    from deblurgs_b200.params import FusedAdam
+    lib = _lib.load()
+    stores = {}
+    for dev in ("cpu", "cuda"):
+        gp, opt, g = _store(P=3000, M=16, seed=5)
+        if dev == "cuda":
+            for name in NAMES:
+                p = getattr(gp, ATTR[name])
+                q = torch.nn.Parameter(p.detach().cuda())
+                st = opt.state.pop(p)
+                opt.state[q] = {"step": st["step"], "exp_avg": st["exp_avg"].cuda(), "exp_avg_sq": st["exp_avg_sq"].cuda()}
+                [grp for grp in opt.param_groups if grp["name"] == name][0]["params"][0] = q
+                setattr(gp, ATTR[name], q)
+            gp.xyz_gradient_accum, gp.denom, gp.max_radii2D = gp.xyz_gradient_accum.cuda(), gp.denom.cuda(), gp.max_radii2D.cuda()
+        stores[dev] = (gp, opt)
+    # same random offsets on both devices: draw on the CPU, replay on the GPU
+    drawn = []
+    real_normal = torch.normal
+
+    def record(mean, std, generator=None):
+        out = real_normal(mean=mean.cpu(), std=std.cpu(), generator=torch.Generator().manual_seed(len(drawn)))
+        drawn.append(out)
+        return out.to(std.device)
+    before = lib.dgs_launch_count(0)
+    torch.normal = record
+    try:
+        for dev in ("cpu", "cuda"):
+            drawn.clear()
+            gp, opt = stores[dev]
+            gp.percent_dense = 0.01
+            gp.densify_and_prune(max_grad=0.5, extent=20.0)
+    finally:
+        torch.normal = real_normal
+    assert lib.dgs_launch_count(0) - before == 3          # clone, split, prune: one launch each
+    (gc, oc), (gg, og) = stores["cpu"], stores["cuda"]
+    assert gg._xyz.shape[0] == gc._xyz.shape[0] and gg._xyz.shape[0] != 3000
+    for name in NAMES:
+        pc, pg = getattr(gc, ATTR[name]), getattr(gg, ATTR[name])
+        assert pg.is_cuda and isinstance(pg, torch.nn.Parameter) and pg.requires_grad
+        assert torch.allclose(pg.detach().cpu(), pc.detach(), rtol=1e-6, atol=1e-7), name
+        sc, sg = oc.state[pc], og.state[pg]
+        assert torch.equal(sg["exp_avg"].cpu(), sc["exp_avg"]) and torch.equal(sg["exp_avg_sq"].cpu(), sc["exp_avg_sq"])
+        assert float(sg["step"]) == float(sc["step"])
+    assert torch.equal(gg.max_radii2D.cpu(), gc.max_radii2D) and torch.equal(gg.denom.cpu(), gc.denom)
+    # and the rebuilt store still trains: one fused Adam step over the new tensors
+    for name in NAMES:
+        p = getattr(gg, ATTR[name])
+        p.grad = torch.ones_like(p)
+    og.step()
