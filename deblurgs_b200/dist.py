@@ -69,9 +69,34 @@ class FlatGradBuffer:
         return self.flat
 
 
+@torch.no_grad()
+def all_reduce_densification_stats(stats):
+    """Make the densification statistics of a step identical on every rank, so that the replicated Gaussian stores
+    densify / prune identically.  Works for both shardings: ranks holding different sub-frames of one view, or
+    different views of a batch -- the reference accumulates sums over whatever it rendered (train.py:188-193:
+    gradient norms and visible fractions add up, radii take the maximum), so: SUM, SUM, MAX.
+    `stats` = rasterizer.DensificationStats (filled by the backward pass); modified in place and returned."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return stats
+    if not stats.ready:
+        raise RuntimeError("densification statistics are produced by the backward pass: call loss.backward() first")
+    sums = torch.cat((stats.grad_norm_sum.reshape(-1), stats.visible_count.reshape(-1)))
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    P = stats.grad_norm_sum.shape[0]
+    stats.grad_norm_sum = sums[:P].reshape(P, 1)
+    stats.visible_count = sums[P:].reshape(P, 1)
+    radius = stats.max_radius.clone()
+    dist.all_reduce(radius, op=dist.ReduceOp.MAX)
+    stats.max_radius = radius
+    return stats
+
+
 def render_blurry_sharded(cmm, cam_idx, background, nu=None):
     """Sub-frame-sharded blurry view: this rank renders its block of the F sub-frames of image
-    `cam_idx`; returns (blurred [3,H,W] identical on every rank, local package, (start, stop))."""
+    `cam_idx`; returns (blurred [3,H,W] identical on every rank, local package, (start, stop)).
+    Densification: the local package's statistics cover this rank's sub-frames only (already normalised by the
+    view's full sub-frame count); call `all_reduce_densification_stats(pkg["densification"])` after backward and
+    before `add_densification_stats_blurry(pkg)` so that every rank accumulates the whole view."""
     from . import renderer
     rank, ws = world()
     view, proj, campos = cmm.get_trajectory_tensors(cam_idx, nu)

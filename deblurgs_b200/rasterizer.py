@@ -291,7 +291,9 @@ class _RasterizeBlurry(torch.autograd.Function):
             rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D, gb, ctx.denom,
             holder is not None)
         if holder is not None:
-            holder.fill(stats, F)
+            # denominator of the view's blur = number of sub-frames of the WHOLE view (a rank that renders a shard of
+            # the sub-frames still normalises its visible-count by all of them, train.py:193: 1 / len(render_pkgs))
+            holder.fill(stats, ctx.denom)
         return (dmeans3D, dmeans2D, dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
                 dview, dproj, None, None, None, None)
 
@@ -312,7 +314,7 @@ class DensificationStats:
         self.grad_norm_sum = stats[:, 0:1]
         self.visible_count = stats[:, 1:2]
         self.max_radius = stats[:, 2].to(torch.int32)
-        self.num_subframes = F
+        self.num_subframes = F      # sub-frames of the whole view (the blur denominator), also on a sub-frame shard
 
     @property
     def ready(self):

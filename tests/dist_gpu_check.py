@@ -33,7 +33,8 @@ def main():
         if sharded:
             blurred, pkg, (a, b) = dd.render_blurry_sharded(cmm, 0, w["bg"])
         else:
-            blurred = cmm.query(0, "all", background=w["bg"])["blurred"]
+            out = cmm.query(0, "all", background=w["bg"])
+            blurred = out["blurred"]
         # smooth (L2) loss for the equality check: with L1, sign(blurred - gt) flips on the handful of
         # pixels where the two summation orders of the blurred image straddle gt (seen at 1080p: a few
         # Gaussians move by ~1e-3 of the max gradient although both paths are exact)
@@ -43,9 +44,12 @@ def main():
         if sharded and world > 1:
             for t in grads:
                 dist.all_reduce(t)
-        return blurred.detach(), loss.detach(), grads
+        stats = (pkg if sharded else out["batched"])["densification"]
+        if sharded:
+            dd.all_reduce_densification_stats(stats)
+        return blurred.detach(), loss.detach(), grads, stats
 
-    b1, l1, g1 = run(True)
+    b1, l1, g1, s1 = run(True)
     # timing of the sharded step (max over ranks)
     torch.cuda.synchronize(); dist.barrier() if world > 1 else None
     t0 = time.perf_counter()
@@ -56,7 +60,11 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if rank == 0:
-        b0, l0, g0 = run(False)
+        b0, l0, g0, s0 = run(False)
+        # densification statistics of the sharded view (all-reduced) = those of the unsharded render
+        assert s1.num_subframes == s0.num_subframes
+        assert torch.equal(s1.visible_count, s0.visible_count) and torch.equal(s1.max_radius, s0.max_radius)
+        assert ((s1.grad_norm_sum - s0.grad_norm_sum).abs().max() / s0.grad_norm_sum.abs().max()).item() <= 1e-3
         err_img = (b0 - b1).abs().max().item()
         rel = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item() for a, b in zip(g1, g0))
         print("config %s world %d: sharded step %.2f ms; blurred max-abs diff %.2e; loss %.6f vs %.6f; "

@@ -51,6 +51,26 @@ def _worker(rank, world, port, q):
         tot = sum(r + 1 for r in range(world))
         assert torch.allclose(p1.grad, torch.full((5, 3), float(tot)))
         assert torch.allclose(p2.grad, torch.full((4,), 10.0 * tot))
+        # densification statistics of a sub-frame-sharded view: every rank ends up with the whole view's statistics
+        # (sums add, radii take the maximum), normalised by the view's FULL sub-frame count on every rank
+        from deblurgs_b200.rasterizer import DensificationStats
+        from deblurgs_b200.motion import GaussianParams
+        P = 6
+        gen = torch.Generator().manual_seed(3)
+        per_sub = torch.rand(F, P, 3, generator=gen)                    # (norm, visible, radius) of every sub-frame
+        per_sub[..., 1] = (per_sub[..., 1] > 0.4).float()
+        per_sub[..., 2] = (per_sub[..., 2] * 50).floor()
+        local = torch.stack([per_sub[a:b, :, 0].sum(0), per_sub[a:b, :, 1].sum(0), per_sub[a:b, :, 2].max(0).values], 1)
+        st = DensificationStats()
+        st.fill(local, float(F))
+        dd.all_reduce_densification_stats(st)
+        assert torch.allclose(st.grad_norm_sum[:, 0], per_sub[:, :, 0].sum(0), atol=1e-6)
+        assert torch.equal(st.visible_count[:, 0], per_sub[:, :, 1].sum(0))
+        assert torch.equal(st.max_radius, per_sub[:, :, 2].max(0).values.to(torch.int32))
+        gp = GaussianParams(torch.zeros(P, 3), torch.zeros(P, 1, 3), torch.zeros(P, 3, 3), torch.zeros(P, 3),
+                            torch.ones(P, 4), torch.zeros(P, 1), 1)
+        gp.add_densification_stats_blurry({"densification": st})
+        assert torch.allclose(gp.denom[:, 0], per_sub[:, :, 1].sum(0) / F)      # 1 / len(render_pkgs) of the whole view
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
