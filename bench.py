@@ -427,6 +427,14 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the c3 / c4 lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: everything else any library prints while the run lasts (NCCL's version
+    # banner, torch warnings) goes to stderr at the file-descriptor level; `emit` writes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference" and rank != 0:
@@ -446,7 +454,7 @@ def main():
     else:
         lib = None
         if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "diff_gaussian_rasterization")):
-            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed"}))
+            emit({"impl": "reference", "unavailable": "baseline/_ref is not installed"})
             return
         step = make_step_reference(w, lam)
 
@@ -569,12 +577,12 @@ def main():
                                "sample": "full workload; the reference implementation of this path is itself a "
                                          "CUDA extension, so this arm runs on the GPU, host cores only drive it"}
         out["gpu_launches"] = 0
-        print(json.dumps(out))
+        emit(out)
         return
 
     out["gpu_launches"] = launches
     if prof is None:      # sub-frame-sharded run: no per-stage breakdown
-        print(json.dumps(out))
+        emit(out)
         return
     st = workload_stats(w)
     tb, sb = C.c_int(0), C.c_int(0)
@@ -633,7 +641,7 @@ def main():
                             "identifyTileRanges (SURVEY 8d); moved = what dgs_binning.cu reads and writes"}}
     if not args.no_cpu_baseline and eff_world == 1:
         out["cpu_baseline"] = cpu_baseline(args.config)
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

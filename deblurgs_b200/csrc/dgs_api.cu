@@ -98,6 +98,7 @@ GeomLayout geom_layout(size_t P, size_t F)
     L.geo0 = o; o = align_up(o + N * sizeof(float4));
     L.geo1 = o; o = align_up(o + N * sizeof(float4));
     L.geo2 = o; o = align_up(o + N * sizeof(float4));
+    L.cmask = o; o = align_up(o + N);
     // binning state
     L.status = o; o = align_up(o + sizeof(BinStatus));
     L.seg_start = o; o = align_up(o + (F + 1) * sizeof(uint32_t));
@@ -195,6 +196,7 @@ static void bind_geom(FwdParams& p, char* geom, const GeomLayout& G)
     p.geo0 = (float4*)(geom + G.geo0);
     p.geo1 = (float4*)(geom + G.geo1);
     p.geo2 = (float4*)(geom + G.geo2);
+    p.cmask = (uint8_t*)(geom + G.cmask);
     p.rect = (uint2*)(geom + G.rect);
     p.dkeys = (uint32_t*)(geom + G.dkeys);
 }
@@ -544,6 +546,8 @@ int dgs_blur_backward(
     b.blur_denominator = blur_denominator;
     char* sc = aligned128(scratch);
     b.g0 = (float4*)sc;
+    b.g1 = b.g0 + N;
+    b.g2 = b.g1 + N;
     b.pose_acc = (double*)(sc + align_up(N * 12 * sizeof(float)));
     b.dL_dmeans2D = dL_dmeans2D; b.dL_dmeans3D = dL_dmeans3D; b.dL_dsh = dL_dsh; b.dL_dopacity = dL_dopacity;
     b.dL_dscales = dL_dscales; b.dL_drotations = dL_drotations;

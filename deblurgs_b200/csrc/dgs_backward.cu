@@ -78,10 +78,10 @@ struct HalvingReduce {
 // tile blending, backward.  grid = (tiles_x, tiles_y * 8/BWD_WARPS, F), BWD_THREADS threads = one
 // 16 x 8 strip of a tile; each warp owns an 8x4 pixel rectangle and, like the forward, evaluates
 // only the staged entries whose alpha >= 1/255 footprint can reach that rectangle.
-// grad = AoS float[N][12]:
-//   0,1 dmean2D(x,y) | 2,3,4 dconic(x,y,w) | 5 dopacity | 6 ddepth | 7 unused | 8,9,10 dcolor | 11 unused
-// (geometry in the first 32-B sector, colour alone in the second: each half of the per-Gaussian backward
-// touches one sector per record)
+// gradient scratch = three planes of N float4:
+//   g0: dmean2D(x,y), dconic(x,y) | g1: dconic(w), dopacity, ddepth, - | g2: dcolor(r,g,b), -
+// (the geometry half of the per-Gaussian backward reads g0 and g1, the colour half g2: every sector it touches is
+// fully used; as one 48-B record per entry the two halves together pulled 80 B per entry)
 //
 // Gradient accumulation is split in two phases so that no per-entry cross-lane reduction is
 // needed (the reference issues 10 atomics per contributing pixel; a per-entry warp reduction
@@ -125,7 +125,7 @@ struct BwdSmem {
 __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned lane, int qn, float wx0f,
                                           float wy0f, float ddelx_dx, float ddely_dy,
                                           const float4* __restrict__ geo0, const float4* __restrict__ geo1,
-                                          char* __restrict__ grad_s)
+                                          float4* __restrict__ gp0, float4* __restrict__ gp1, float4* __restrict__ gp2)
 {
     __syncwarp();
     const unsigned e = lane & 15u, half = lane >> 4;
@@ -164,16 +164,16 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
     Cb += __shfl_xor_sync(FULL_MASK, Cb, 16);   Cd += __shfl_xor_sync(FULL_MASK, Cd, 16);
     if (half == 0 && live) {
         const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
-        float* rec = reinterpret_cast<float*>(grad_s + (size_t)id * 48u);
-        // three 16-B vector reductions per 48-B record (sm_90+ red.global.add.v4.f32) instead of ten scalar ones
-        red_add_v4(rec + 0, -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy, -0.5f * Sxx, -0.5f * Sxy);
-        red_add_v4(rec + 4, -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, 0.f);
-        red_add_v4(rec + 8, Cr, Cg, Cb, 0.f);
+        // three 16-B vector reductions (sm_90+ red.global.add.v4.f32), one per gradient plane, instead of ten scalar ones
+        red_add_v4(reinterpret_cast<float*>(gp0 + id), -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy,
+                   -0.5f * Sxx, -0.5f * Sxy);
+        red_add_v4(reinterpret_cast<float*>(gp1 + id), -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, 0.f);
+        red_add_v4(reinterpret_cast<float*>(gp2 + id), Cr, Cg, Cb, 0.f);
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, float* __restrict__ grad)
+__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
     const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
     const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
     const float4* __restrict__ geo2 = f.geo2 + (size_t)s * f.P;
-    char* __restrict__ grad_s = reinterpret_cast<char*>(grad + (size_t)s * f.P * 12);
+    float4* __restrict__ gp0 = p.g0 + (size_t)s * f.P;
+    float4* __restrict__ gp1 = p.g1 + (size_t)s * f.P;
+    float4* __restrict__ gp2 = p.g2 + (size_t)s * f.P;
 
     const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
     float T = T_final;
@@ -328,13 +330,13 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p, f
                 sm.qw[warp][qn][lane] = make_float2(w1, w2);
                 sm.qid[warp][qn] = lds_u32(a_id + 4u * (uint32_t)j);   // same value from every lane
                 if (++qn == BWD_QN) {
-                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, grad_s);
+                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
                     qn = 0;
                 }
             }
         }
     }
-    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, grad_s);
+    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
@@ -347,7 +349,7 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
         configured = true;
     }
     dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
-    k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p, reinterpret_cast<float*>(p.g0));
+    k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -366,7 +368,7 @@ __device__ static const int kPoseSlot[NPOSE] = {0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 
 // gradients, densification statistics).  PRECOMP: colours were supplied precomputed, their gradient
 // is a plain sum over sub-frames and rides along here; otherwise the SH half (k_sh_bwd) handles colour.
 template <bool PRECOMP>
-__global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdParams p, const float* __restrict__ grad)
+__global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdParams p)
 {
     const FwdParams& f = p.f;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,9 +409,9 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
         Stage t;
         const size_t n = (size_t)s * f.P + gi;
         t.radius = live ? f.radii[n] : 0;
-        t.a = reinterpret_cast<const float4*>(grad)[n * 3];
-        t.b = reinterpret_cast<const float4*>(grad)[n * 3 + 1];
-        t.c = PRECOMP ? reinterpret_cast<const float4*>(grad)[n * 3 + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+        t.a = p.g0[n];
+        t.b = p.g1[n];
+        t.c = PRECOMP ? p.g2[n] : make_float4(0.f, 0.f, 0.f, 0.f);
         return t;
     };
     Stage pf[GEO_PF];
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
 #define SH_BWD_THREADS 128
 
 template <int DEG>
-__global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p, const float* __restrict__ grad)
+__global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
 {
     const FwdParams& f = p.f;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -642,9 +644,9 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p,
         Stage t;
         const size_t n = (size_t)s * f.P + gi;
         t.radius = live ? f.radii[n] : 0;
-        const float4 c = reinterpret_cast<const float4*>(grad)[n * 3 + 2];   // (dL/dr, dL/dg, dL/db, -): one sector
+        const float4 c = p.g2[n];   // (dL/dr, dL/dg, dL/db, -): its own plane, fully used sectors
         t.cr = c.x; t.cg = c.y; t.cb = c.z;
-        t.mask = __float_as_uint(reinterpret_cast<const float*>(f.geo2 + n)[3]);
+        t.mask = f.cmask[n];
         return t;
     };
     Stage pf[BWD_PF];
@@ -786,18 +788,17 @@ void launch_preprocess_bwd(const BwdParams& p, int sh_degree, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.P > 0 && f.F > 0) {
-        const float* grad = reinterpret_cast<const float*>(p.g0);
         dim3 grid((f.P + PRE_BWD_THREADS - 1) / PRE_BWD_THREADS), block(PRE_BWD_THREADS);
         if (f.colors_precomp != nullptr) {
-            k_preprocess_bwd<true><<<grid, block, 0, st>>>(p, grad);
+            k_preprocess_bwd<true><<<grid, block, 0, st>>>(p);
         } else {
-            k_preprocess_bwd<false><<<grid, block, 0, st>>>(p, grad);
+            k_preprocess_bwd<false><<<grid, block, 0, st>>>(p);
             dim3 sgrid((f.P + SH_BWD_THREADS - 1) / SH_BWD_THREADS), sblock(SH_BWD_THREADS);
             switch (sh_degree) {
-                case 0: k_sh_bwd<0><<<sgrid, sblock, 0, st>>>(p, grad); break;
-                case 1: k_sh_bwd<1><<<sgrid, sblock, 0, st>>>(p, grad); break;
-                case 2: k_sh_bwd<2><<<sgrid, sblock, 0, st>>>(p, grad); break;
-                default: k_sh_bwd<3><<<sgrid, sblock, 0, st>>>(p, grad); break;
+                case 0: k_sh_bwd<0><<<sgrid, sblock, 0, st>>>(p); break;
+                case 1: k_sh_bwd<1><<<sgrid, sblock, 0, st>>>(p); break;
+                case 2: k_sh_bwd<2><<<sgrid, sblock, 0, st>>>(p); break;
+                default: k_sh_bwd<3><<<sgrid, sblock, 0, st>>>(p); break;
             }
         }
     }

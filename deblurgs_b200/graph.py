@@ -61,6 +61,11 @@ class BlurryViewGraph:
 
     def _capture(self, capacity):
         lib = _lib.load()
+        # (the parameters' AccumulateGrad nodes were created on the caller's stream, warm-up and capture run on side
+        # streams: expected here, and everything is ordered by the stream waits / the capture itself)
+        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if warn is not None:
+            warn(False)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
