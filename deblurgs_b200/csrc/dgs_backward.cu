@@ -306,8 +306,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
                         alpha = min(0.99f, con_o.w * G);
                     }
                 }
-                const bool contrib = alpha >= 1.0f / 255.0f;
-                if (!__any_sync(FULL_MASK, contrib)) continue;
+                const bool contrib = alpha >= 1.0f / 255.0f;     // (some lane contributes: the forward said so)
                 float w1 = 0.f, w2 = 0.f;
                 if (contrib) {
                     // The reference replays T and the colour accumulated BEHIND the entry as normalised
@@ -619,7 +618,21 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
     __shared__ float4 s_sh[NV][SH_BWD_THREADS];
 
     const float3 mean = {f.means3D[3 * gi], f.means3D[3 * gi + 1], f.means3D[3 * gi + 2]};
-    {
+    // The block's coefficients are one contiguous run of global memory when every allocated coefficient is active
+    // (M == NC): the block loads it with coalesced 16-B loads and transposes it into the per-thread columns; per-thread
+    // loads of a 192-B row touch 32 different sectors per instruction.
+    const bool dense = f.M == NC && (3 * NC) % 4 == 0 && (reinterpret_cast<uintptr_t>(f.shs) & 15) == 0;
+    if (dense) {
+        const size_t g0 = (size_t)blockIdx.x * SH_BWD_THREADS;
+        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)f.P - g0);
+        const float4* src4 = reinterpret_cast<const float4*>(f.shs + g0 * 3 * NC);
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int i = k * SH_BWD_THREADS + threadIdx.x;          // float4 index inside the block's run
+            if (i < rows * NV) s_sh[i % NV][i / NV] = __ldg(src4 + i);
+        }
+        __syncthreads();
+    } else {
         const float* src = f.shs + (size_t)gi * f.M * 3;
         float tmp[4 * NV];
 #pragma unroll
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
         for (int v = 0; v < NV; v++)
             s_sh[v][threadIdx.x] = make_float4(tmp[4 * v], tmp[4 * v + 1], tmp[4 * v + 2], tmp[4 * v + 3]);
     }
-    // only this thread reads its column back: no barrier needed
+    // (non-dense path: only this thread reads its column back, no barrier needed)
     const uint32_t a_sh = smem_addr(&s_sh[0][threadIdx.x]);
     // coefficient k, channel ch = float 3k+ch of the column; SHV(v) re-reads float4 slot v (volatile: the
     // compiler must not hoist the 48 values back into registers)
@@ -757,12 +770,31 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
         }
     }
 #undef SHV
-    if (!live) return;
-    float* dst = p.dL_dsh + (size_t)g * f.M * 3;
+    if (dense && (reinterpret_cast<uintptr_t>(p.dL_dsh) & 15) == 0) {
+        // the same transposition on the way out: dL/dsh rows through the (now free) columns, coalesced 16-B stores
+        __syncthreads();
+        float flat[4 * NV];
 #pragma unroll
-    for (int k = 0; k < NC; k++) { dst[3 * k] = dsh[k][0]; dst[3 * k + 1] = dsh[k][1]; dst[3 * k + 2] = dsh[k][2]; }
-    for (int k = NC; k < f.M; k++) { dst[3 * k] = 0.f; dst[3 * k + 1] = 0.f; dst[3 * k + 2] = 0.f; }
-    if (DEG > 0) {
+        for (int k = 0; k < NC; k++) { flat[3 * k] = dsh[k][0]; flat[3 * k + 1] = dsh[k][1]; flat[3 * k + 2] = dsh[k][2]; }
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            s_sh[v][threadIdx.x] = make_float4(flat[4 * v], flat[4 * v + 1], flat[4 * v + 2], flat[4 * v + 3]);
+        __syncthreads();
+        const size_t g0 = (size_t)blockIdx.x * SH_BWD_THREADS;
+        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)f.P - g0);
+        float4* dst4 = reinterpret_cast<float4*>(p.dL_dsh + g0 * 3 * NC);
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const int i = k * SH_BWD_THREADS + threadIdx.x;
+            if (i < rows * NV) dst4[i] = s_sh[i % NV][i / NV];
+        }
+    } else if (live) {
+        float* dst = p.dL_dsh + (size_t)g * f.M * 3;
+#pragma unroll
+        for (int k = 0; k < NC; k++) { dst[3 * k] = dsh[k][0]; dst[3 * k + 1] = dsh[k][1]; dst[3 * k + 2] = dsh[k][2]; }
+        for (int k = NC; k < f.M; k++) { dst[3 * k] = 0.f; dst[3 * k + 1] = 0.f; dst[3 * k + 2] = 0.f; }
+    }
+    if (live && DEG > 0) {
         p.dL_dmeans3D[3 * g] += dmean.x; p.dL_dmeans3D[3 * g + 1] += dmean.y; p.dL_dmeans3D[3 * g + 2] += dmean.z;
     }
 }
