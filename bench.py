@@ -147,34 +147,21 @@ def flat_grad_views(params):
 
 
 def make_step_ours(w, world, lambda_t_smooth=0.0, use_graph=False):
+    """views-dp step.  world > 1: the Gaussian gradients go into a flat buffer that doubles as the backward's gradient
+    SINK (deblurgs_b200.dist.FlatGradBuffer.for_gaussians): rows are all-reduced over NCCL while the rest of the
+    per-Gaussian backward still runs; the step ends when the last collective has landed."""
+    from deblurgs_b200 import dist as dd
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     gparams = g.parameters()
     cparams = cmm.parameters()
-    flat = flat_grad_views(gparams) if world > 1 else None
+    sink = None
+    if world > 1:
+        sink = dd.FlatGradBuffer.for_gaussians(g)
+        g.grad_sink = sink
 
-    if use_graph:
-        from deblurgs_b200.graph import BlurryViewGraph
-        graph = BlurryViewGraph(cmm, 0, w["bg"], (3, w["H"], w["W"]), lambda_t_smooth,
-                                pre_backward=(flat.zero_ if flat is not None else None),
-                                caller_owned_grads=(gparams if flat is not None else ()))
-
-        def step(gt, gt_ready=None):
-            if gt_ready is not None:   # ground truth uploaded on a side stream
-                torch.cuda.current_stream().wait_event(gt_ready)
-            graph.gt.copy_(gt, non_blocking=True)
-            loss = graph.replay()
-            if flat is not None:
-                import torch.distributed as dist
-                dist.all_reduce(flat)
-            return loss
-        step.graph = graph
-        return step
-
-    def step(gt, gt_ready=None):
-        if flat is not None:
-            flat.zero_()
-        else:
+    def eager(gt, gt_ready=None):
+        if sink is None:
             for p in gparams:
                 p.grad = None
         for p in cparams:
@@ -185,34 +172,59 @@ def make_step_ours(w, world, lambda_t_smooth=0.0, use_graph=False):
         # mean |blurred - gt| (+ lambda * mean |subframes[1:] - subframes[:-1]| for --loss smooth), fused
         loss = blur_photometric_loss(out["blurred"], out["subframes"], gt, lambda_t_smooth)
         loss.backward()
-        if flat is not None:
-            import torch.distributed as dist
-            dist.all_reduce(flat)
+        if sink is not None:
+            sink.wait()
         return loss
-    step.graph = None
+    eager.graph = None
+    eager.mode = "kernel by kernel"
+    if not use_graph:
+        return eager
+
+    from deblurgs_b200.graph import BlurryViewGraph
+    try:
+        graph = BlurryViewGraph(cmm, 0, w["bg"], (3, w["H"], w["W"]), lambda_t_smooth,
+                                caller_owned_grads=(gparams if sink is not None else ()),
+                                post_backward=(sink.wait if sink is not None else None))
+    except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build: launch kernel by kernel
+        sys.stderr.write("CUDA-graph capture failed (%s: %s); falling back to kernel-by-kernel launches\n"
+                         % (type(e).__name__, str(e)[:300]))
+        torch.cuda.synchronize()
+        return eager
+
+    def step(gt, gt_ready=None):
+        if gt_ready is not None:   # ground truth uploaded on a side stream
+            torch.cuda.current_stream().wait_event(gt_ready)
+        graph.gt.copy_(gt, non_blocking=True)
+        return graph.replay()
+    step.graph = graph
+    step.mode = "cuda-graph replay (one launch per step" + (", NCCL all-reduces inside the graph)" if sink is not None else ")")
     return step
 
 
 def make_step_subframe_sharded(w, world):
     """One blurry view, its sub-frames sharded over the ranks (deblurgs_b200.dist.render_blurry_sharded): partial
-    blurred images summed by an all-reduce, every rank evaluates the same L1 loss, Gaussian and trajectory
-    gradients summed by an all-reduce of one flat buffer."""
+    blurred images summed by an all-reduce, every rank evaluates the same L1 loss; the Gaussian gradients are summed
+    through the gradient sink (all-reduce of finished rows under the rest of the backward), the trajectory gradients
+    by one small all-reduce."""
     from deblurgs_b200 import dist as dd
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
-    params = g.parameters() + cmm.parameters()
-    flat = flat_grad_views(params)
+    sink = dd.FlatGradBuffer.for_gaussians(g)
+    g.grad_sink = sink
+    cflat = flat_grad_views(cmm.parameters())
 
     def step(gt, gt_ready=None):
-        flat.zero_()
+        cflat.zero_()
         blurred, pkg, _ = dd.render_blurry_sharded(cmm, 0, w["bg"])
         loss = blur_photometric_loss(blurred, pkg["render"], gt, 0.0)
         loss.backward()
+        sink.wait()
         if world > 1:
             import torch.distributed as dist
-            dist.all_reduce(flat)
+            dist.all_reduce(cflat)
         return loss
     step.graph = None
+    step.mode = "kernel by kernel"
     return step
 
 
@@ -393,6 +405,8 @@ def other_config(name, rank, world, device, steps=3, warmup=3):
     strong = name == "c3"
     w = build_workload(name, 0 if strong else rank, device)
     step = make_step_subframe_sharded(w, world) if (strong and world > 1) else make_step_ours(w, 1 if strong else world)
+    mode = ("subframes-sharded-%d (NCCL all-reduce of the blurred image; gradient all-reduce overlapped with the backward)"
+            % world) if (strong and world > 1) else None
     gt = w["gt_host"].to(device)
     for _ in range(warmup):
         step(gt)
@@ -402,8 +416,7 @@ def other_config(name, rank, world, device, steps=3, warmup=3):
     del w, step
     torch.cuda.empty_cache()
     return {"workload": "%s: %d Gaussians, %dx%d, num_subframes=%d" % (name, P, W, H, F),
-            "parallelism": ("subframes-sharded-%d (NCCL all-reduce of the blurred image + gradients)" % world) if strong
-            else "views-dp%d" % world,
+            "parallelism": mode if mode else ("single GPU" if strong else "views-dp%d" % world),
             "scaling": "strong" if strong else "weak", "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "value": (1.0 if strong else world) * 1000.0 / ms, "unit": UNIT, "loss_last": loss}
 
@@ -511,10 +524,10 @@ def main():
     # ---- per-stage CUDA-event times: a separate pass, kernel by kernel (events inside a replayed graph cannot be read)
     prof = None
     if lib is not None and not sharded:
-        eager = make_step_ours(w, 1, lam, False) if use_graph else step
-        if use_graph:
-            for p in w["gaussians"].parameters():
-                p.grad = None
+        w["gaussians"].grad_sink = None
+        eager = make_step_ours(w, 1, lam, False)
+        for p in w["gaussians"].parameters():
+            p.grad = None
         for _ in range(2):
             eager(gt_dev)
         torch.cuda.synchronize()
@@ -559,7 +572,7 @@ def main():
                                   "L1 loss" if lam == 0.0 else "L1 + 1e-3 temporal-smoothness loss"),
                    "parallelism": par},
         "loss_last": loss_host,
-        "launch_mode": "cuda-graph replay (one launch per step)" if use_graph else "kernel by kernel",
+        "launch_mode": getattr(step, "mode", "kernel by kernel"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(w["gt_host"].numel() * 4),
                 "d2h_bytes_per_step": 4 + (24 if use_graph else 0),

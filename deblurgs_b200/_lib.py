@@ -38,6 +38,8 @@ SIGNATURES = {
     "dgs_blur_backward_scratch_bytes": (C.c_size_t, [_i, _i]),
     "dgs_blur_backward": (_i, [_i, _i, _i, _i, _i64] + _FWD_COMMON +
                           [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p] + [_p] * 11 + [_p]),
+    "dgs_blur_backward_range": (_i, [_i, _i, _i, _i, _i64] + _FWD_COMMON +
+                                [_i, _p, _p, _p, _p, _p, _p, _p, _f, _p] + [_p] * 11 + [_i64, _i64, _i, _p]),
     "dgs_forward": (_i, [ALLOC_FN, _p, ALLOC_FN, _p, ALLOC_FN, _p,
                          _i, _i, _i] + _FWD_COMMON + [_i, _i, _p, _p, _p, C.POINTER(_i64), _p]),
     "dgs_backward": (_i, [_i, _i, _i, _i64] + _FWD_COMMON +

@@ -489,7 +489,7 @@ size_t dgs_blur_backward_scratch_bytes(int P, int F)
     return align_up(N * 12 * sizeof(float)) + align_up((size_t)F * 32 * sizeof(double)) + 256;
 }
 
-int dgs_blur_backward(
+int dgs_blur_backward_range(
     int P, int F, int sh_degree, int sh_coeffs, int64_t num_rendered,
     const float* background, int width, int height,
     const float* means3D, const float* shs, const float* colors_precomp,
@@ -503,9 +503,11 @@ int dgs_blur_backward(
     char* scratch,
     float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
-    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats, void* stream)
+    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats,
+    int64_t g_begin, int64_t g_end, int stages, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_begin < 0 || g_end > P || g_begin > g_end) return fail(DGS_ERR_INVALID_ARGUMENT, "bad Gaussian range");
     BwdParams b;
     memset(&b, 0, sizeof(b));
     int rc = fill_params(b.f, P, F, sh_coeffs, background, width, height, means3D, shs, colors_precomp,
@@ -515,8 +517,10 @@ int dgs_blur_backward(
     if (F == 0) return DGS_OK;
     if (!dL_dviewmatrix || !dL_dprojmatrix) return fail(DGS_ERR_INVALID_ARGUMENT, "null pose gradient output");
     if (P == 0) {
-        DGS_CUDA(cudaMemsetAsync(dL_dviewmatrix, 0, (size_t)F * 16 * sizeof(float), st), "memset");
-        DGS_CUDA(cudaMemsetAsync(dL_dprojmatrix, 0, (size_t)F * 16 * sizeof(float), st), "memset");
+        if (stages & DGS_BWD_FINISH) {
+            DGS_CUDA(cudaMemsetAsync(dL_dviewmatrix, 0, (size_t)F * 16 * sizeof(float), st), "memset");
+            DGS_CUDA(cudaMemsetAsync(dL_dprojmatrix, 0, (size_t)F * 16 * sizeof(float), st), "memset");
+        }
         return DGS_OK;
     }
     if (!geom_buffer || !binning_buffer || !image_buffer || !scratch || !radii)
@@ -554,16 +558,49 @@ int dgs_blur_backward(
     b.dL_dcolors_precomp = dL_dcolors_precomp; b.dL_dcov3D_precomp = dL_dcov3D_precomp;
     b.dL_dview = dL_dviewmatrix; b.dL_dproj = dL_dprojmatrix;
     b.densify_stats = densify_stats;
+    b.g_begin = (int)g_begin;
+    b.g_end = (int)g_end;
 
-    {
-        StageTimer t(ST_BWD_MEMSET, st, 0);
-        DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
+    if (stages & DGS_BWD_BLEND) {
+        {
+            StageTimer t(ST_BWD_MEMSET, st, 0);
+            DGS_CUDA(cudaMemsetAsync(sc, 0, align_up(N * 12 * sizeof(float)) + (size_t)F * 32 * sizeof(double), st), "grad memset");
+        }
+        // num_rendered is informational (the lists are delimited by the per-tile ranges); < 0 = unknown (speculative forward)
+        if (num_rendered != 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
     }
-    // num_rendered is informational (the lists are delimited by the per-tile ranges); < 0 = unknown (speculative forward)
-    if (num_rendered != 0 && pixels > 0) { StageTimer t(ST_RENDER_BWD, st, 1); launch_render_bwd(b, st); }
-    { StageTimer t(ST_PREPROCESS_BWD, st, colors_precomp ? 2 : 3); launch_preprocess_bwd(b, sh_degree, st); }
+    if ((stages & DGS_BWD_GAUSSIANS) && g_end > g_begin) {
+        StageTimer t(ST_PREPROCESS_BWD, st, colors_precomp ? 1 : 2);
+        launch_preprocess_bwd(b, sh_degree, st);
+    }
+    if (stages & DGS_BWD_FINISH) { StageTimer t(ST_PREPROCESS_BWD, st, 1); launch_pose_finalize(b, st); }
     DGS_CUDA(cudaGetLastError(), "backward launch");
     return DGS_OK;
+}
+
+int dgs_blur_backward(
+    int P, int F, int sh_degree, int sh_coeffs, int64_t num_rendered,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
+    const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpixdepth, const float* dL_dblur, float blur_denominator,
+    char* scratch,
+    float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
+    float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
+    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats, void* stream)
+{
+    return dgs_blur_backward_range(P, F, sh_degree, sh_coeffs, num_rendered, background, width, height, means3D, shs,
+                                   colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp,
+                                   viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, z_near, z_far, use_sigmoid, radii,
+                                   geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpixdepth, dL_dblur,
+                                   blur_denominator, scratch, dL_dmeans2D, dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales,
+                                   dL_drotations, dL_dcolors_precomp, dL_dcov3D_precomp, dL_dviewmatrix, dL_dprojmatrix,
+                                   densify_stats, 0, P, DGS_BWD_ALL, stream);
 }
 
 int dgs_forward(

@@ -370,9 +370,9 @@ template <bool PRECOMP>
 __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdParams p)
 {
     const FwdParams& f = p.f;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = p.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
-    const bool live = g < f.P;
+    const bool live = g < p.g_end;
     const int gi = live ? g : 0;
 
     const float3 mean = {f.means3D[3 * gi], f.means3D[3 * gi + 1], f.means3D[3 * gi + 2]};
@@ -610,8 +610,8 @@ template <int DEG>
 __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
 {
     const FwdParams& f = p.f;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = g < f.P;
+    const int g = p.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = g < p.g_end;
     const int gi = live ? g : 0;
     constexpr int NC = (DEG + 1) * (DEG + 1);
     constexpr int NV = (3 * NC + 3) / 4;          // float4 slots per Gaussian
@@ -621,10 +621,11 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
     // The block's coefficients are one contiguous run of global memory when every allocated coefficient is active
     // (M == NC): the block loads it with coalesced 16-B loads and transposes it into the per-thread columns; per-thread
     // loads of a 192-B row touch 32 different sectors per instruction.
-    const bool dense = f.M == NC && (3 * NC) % 4 == 0 && (reinterpret_cast<uintptr_t>(f.shs) & 15) == 0;
+    const bool dense = f.M == NC && (3 * NC) % 4 == 0 && (reinterpret_cast<uintptr_t>(f.shs) & 15) == 0 &&
+                       ((size_t)p.g_begin * 3 * NC) % 4 == 0;
     if (dense) {
-        const size_t g0 = (size_t)blockIdx.x * SH_BWD_THREADS;
-        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)f.P - g0);
+        const size_t g0 = (size_t)p.g_begin + (size_t)blockIdx.x * SH_BWD_THREADS;
+        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)p.g_end - g0);
         const float4* src4 = reinterpret_cast<const float4*>(f.shs + g0 * 3 * NC);
 #pragma unroll
         for (int k = 0; k < NV; k++) {
@@ -780,8 +781,8 @@ __global__ void __launch_bounds__(SH_BWD_THREADS, 4) k_sh_bwd(const BwdParams p)
         for (int v = 0; v < NV; v++)
             s_sh[v][threadIdx.x] = make_float4(flat[4 * v], flat[4 * v + 1], flat[4 * v + 2], flat[4 * v + 3]);
         __syncthreads();
-        const size_t g0 = (size_t)blockIdx.x * SH_BWD_THREADS;
-        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)f.P - g0);
+        const size_t g0 = (size_t)p.g_begin + (size_t)blockIdx.x * SH_BWD_THREADS;
+        const int rows = (int)min((size_t)SH_BWD_THREADS, (size_t)p.g_end - g0);
         float4* dst4 = reinterpret_cast<float4*>(p.dL_dsh + g0 * 3 * NC);
 #pragma unroll
         for (int k = 0; k < NV; k++) {
@@ -819,21 +820,26 @@ __global__ void k_pose_finalize(const double* __restrict__ acc, int F, float* __
 void launch_preprocess_bwd(const BwdParams& p, int sh_degree, cudaStream_t st)
 {
     const FwdParams& f = p.f;
-    if (f.P > 0 && f.F > 0) {
-        dim3 grid((f.P + PRE_BWD_THREADS - 1) / PRE_BWD_THREADS), block(PRE_BWD_THREADS);
-        if (f.colors_precomp != nullptr) {
-            k_preprocess_bwd<true><<<grid, block, 0, st>>>(p);
-        } else {
-            k_preprocess_bwd<false><<<grid, block, 0, st>>>(p);
-            dim3 sgrid((f.P + SH_BWD_THREADS - 1) / SH_BWD_THREADS), sblock(SH_BWD_THREADS);
-            switch (sh_degree) {
-                case 0: k_sh_bwd<0><<<sgrid, sblock, 0, st>>>(p); break;
-                case 1: k_sh_bwd<1><<<sgrid, sblock, 0, st>>>(p); break;
-                case 2: k_sh_bwd<2><<<sgrid, sblock, 0, st>>>(p); break;
-                default: k_sh_bwd<3><<<sgrid, sblock, 0, st>>>(p); break;
-            }
+    const int n = p.g_end - p.g_begin;
+    if (n <= 0 || f.F <= 0) return;
+    dim3 grid((n + PRE_BWD_THREADS - 1) / PRE_BWD_THREADS), block(PRE_BWD_THREADS);
+    if (f.colors_precomp != nullptr) {
+        k_preprocess_bwd<true><<<grid, block, 0, st>>>(p);
+    } else {
+        k_preprocess_bwd<false><<<grid, block, 0, st>>>(p);
+        dim3 sgrid((n + SH_BWD_THREADS - 1) / SH_BWD_THREADS), sblock(SH_BWD_THREADS);
+        switch (sh_degree) {
+            case 0: k_sh_bwd<0><<<sgrid, sblock, 0, st>>>(p); break;
+            case 1: k_sh_bwd<1><<<sgrid, sblock, 0, st>>>(p); break;
+            case 2: k_sh_bwd<2><<<sgrid, sblock, 0, st>>>(p); break;
+            default: k_sh_bwd<3><<<sgrid, sblock, 0, st>>>(p); break;
         }
     }
+}
+
+void launch_pose_finalize(const BwdParams& p, cudaStream_t st)
+{
+    const FwdParams& f = p.f;
     if (f.F > 0) k_pose_finalize<<<(f.F * 32 + 255) / 256, 256, 0, st>>>(p.pose_acc, f.F, p.dL_dview, p.dL_dproj);
 }
 

@@ -48,25 +48,71 @@ def all_reduce_sum(x):
 
 
 class FlatGradBuffer:
-    """One flat fp32 gradient buffer; each parameter's .grad is a view into it, so the whole set of
-    Gaussian gradients (P*(11+3M) floats) moves with a single all-reduce."""
+    """One flat fp32 gradient buffer; each parameter's .grad is a view into it.
 
-    def __init__(self, params):
+    Plain use: `zero()`, backward (autograd accumulates into the views), `all_reduce()` -- one collective.
+    As a gradient SINK of the Gaussian store (`for_gaussians`, handed to `render_blurry(..., grad_sink=)` or set as
+    `gaussians.grad_sink`): the backward writes finished rows straight into the views and calls `rows_done(g0, g1)`,
+    which starts the all-reduce of those rows of the largest tensor (the SH rest coefficients, 3/4 of all bytes) on
+    NCCL's own stream while the next range of Gaussians is still being computed; `finish()` reduces the five small
+    tensors (contiguous in the buffer) in one call; `wait()` makes the current stream wait for all of it."""
+
+    def __init__(self, params, names=None):
         self.params = [p for p in params]
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.views, self.spans = {}, {}
         off = 0
-        for p in self.params:
+        for i, p in enumerate(self.params):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            key = names[i] if names is not None else i
+            self.views[key] = p.grad
+            self.spans[key] = (off, off + p.numel())
             off += p.numel()
+        self.works, self.big, self.small_span = [], None, None
+
+    @classmethod
+    def for_gaussians(cls, g):
+        """Sink layout for a `GaussianParams` store: the five small tensors first (one contiguous block), the SH rest
+        coefficients last."""
+        names = ["xyz", "f_dc", "scaling", "rotation", "opacity", "f_rest"]
+        params = [g._xyz, g._features_dc, g._scaling, g._rotation, g._opacity, g._features_rest]
+        self = cls(params, names)
+        self.big = "f_rest"
+        self.small_span = (0, self.spans["f_rest"][0])
+        return self
 
     def zero(self):
         self.flat.zero_()
 
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
     def all_reduce(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if self._active():
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         return self.flat
+
+    # ---- sink protocol (called from the backward of rasterizer._RenderStoreBlurry) --------------------
+    def begin(self):
+        self.works = []
+
+    def rows_done(self, g0, g1):
+        """Rows [g0, g1) of every Gaussian gradient are final: reduce the big tensor's rows now (asynchronously: the
+        collective runs on NCCL's stream behind everything enqueued so far, the caller's stream goes on)."""
+        if self._active() and self.big is not None and g1 > g0:
+            self.works.append(dist.all_reduce(self.views[self.big][g0:g1], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self):
+        if self._active() and self.small_span is not None:
+            a, b = self.small_span
+            self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, async_op=True))
+
+    def wait(self):
+        """The current stream waits for every collective started since begin()."""
+        for w in self.works:
+            w.wait()
+        self.works = []
 
 
 @torch.no_grad()
@@ -91,7 +137,7 @@ def all_reduce_densification_stats(stats):
     return stats
 
 
-def render_blurry_sharded(cmm, cam_idx, background, nu=None):
+def render_blurry_sharded(cmm, cam_idx, background, nu=None, grad_sink=None):
     """Sub-frame-sharded blurry view: this rank renders its block of the F sub-frames of image
     `cam_idx`; returns (blurred [3,H,W] identical on every rank, local package, (start, stop)).
     Densification: the local package's statistics cover this rank's sub-frames only (already normalised by the
@@ -103,5 +149,6 @@ def render_blurry_sharded(cmm, cam_idx, background, nu=None):
     F = view.shape[0]
     a, b = subframe_shard(F, rank, ws)
     pkg = renderer.render_blurry(view[a:b].contiguous(), proj[a:b].contiguous(), campos[a:b].contiguous(),
-                                 cmm.original_cam[0], cmm.gaussians, background, blur_denominator=float(F))
+                                 cmm.original_cam[0], cmm.gaussians, background, blur_denominator=float(F),
+                                 grad_sink=grad_sink)
     return all_reduce_sum(pkg["blurred"]), pkg, (a, b)

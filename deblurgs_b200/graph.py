@@ -29,7 +29,7 @@ class BlurryViewGraph:
     `parameters` (default: the Gaussians' and the trajectory's) get their .grad from the captured backward."""
 
     def __init__(self, cmm, cam_idx, background, gt_shape, lambda_t_smooth=0.0, parameters=None, pre_backward=None,
-                 caller_owned_grads=(), capacity_margin=1.25):
+                 caller_owned_grads=(), capacity_margin=1.25, post_backward=None):
         self.cmm, self.cam_idx, self.bg, self.lam = cmm, cam_idx, background, float(lambda_t_smooth)
         dev = cmm.gaussians.get_xyz.device
         self.device = dev
@@ -37,6 +37,7 @@ class BlurryViewGraph:
         # pre_backward: optional callable captured in front of the step (e.g. zeroing a flat gradient buffer whose views
         # are the .grad of `caller_owned_grads`: those accumulate in place; every other .grad is produced by the graph)
         self.pre_backward = pre_backward
+        self.post_backward = post_backward        # captured behind the backward (e.g. a gradient sink's wait())
         self.owned = set(id(p) for p in caller_owned_grads)
         self.margin = float(capacity_margin)
         self.gt = torch.zeros(gt_shape, dtype=torch.float32, device=dev)
@@ -52,6 +53,8 @@ class BlurryViewGraph:
         out = self.cmm.query(self.cam_idx, "all", background=self.bg)
         loss = blur_photometric_loss(out["blurred"], out["subframes"], self.gt, self.lam)
         loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
         return out, loss.detach()
 
     def _reset_grads(self):

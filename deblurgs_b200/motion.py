@@ -97,6 +97,7 @@ class GaussianParams(DensificationMixin):
         self.scale_lower_bound = scale_lower_bound
         self.use_isotropic = use_isotropic
         self.optimizer = None
+        self.grad_sink = None      # optional dist.FlatGradBuffer.for_gaussians(self): gradients all-reduced under the backward
 
     @classmethod
     def from_scene(cls, scene, **kw):

@@ -135,10 +135,17 @@ def _forward_batched(means3D, sh, colors_precomp, opacities, scales, rotations, 
     return color, depth, radii, blur, D, geom.t, binning.t, img.t
 
 
+BWD_BLEND, BWD_GAUSSIANS, BWD_FINISH, BWD_ALL = 1, 2, 4, 7
+
+
 def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacities, scales, rotations,
                       cov3Ds_precomp, viewmatrix, projmatrix, campos, bg, H, W, tanfovx, tanfovy,
                       scale_modifier, z_near, z_far, sh_degree, use_sigmoid, radii, geom, binning, img,
-                      grad_color, grad_depth, want_means2D, grad_blur=None, blur_denominator=1.0, want_stats=False):
+                      grad_color, grad_depth, want_means2D, grad_blur=None, blur_denominator=1.0, want_stats=False,
+                      ranges=None, outputs=None, on_range=None):
+    """Runs dgs_blur_backward_range.  ranges: list of (g0, g1) covering [0, P) -- the per-Gaussian stage is launched
+    once per range and `on_range(g0, g1, out)` is called after each (e.g. to start a collective on those rows while
+    the next range computes); outputs: preallocated (dmeans3D, dsh, dopacity, dscales, drot) to write into."""
     lib = _lib.load()
     dev = means3D.device
     f32 = dict(dtype=torch.float32, device=dev)
@@ -150,11 +157,14 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
     # 12 torch::zeros per sub-frame, rasterize_points.cu:163-175)
     alloc = torch.zeros if (P == 0 or F == 0) else torch.empty
     dmeans2D = alloc((F, P, 3), **f32) if want_means2D else None
-    dmeans3D = alloc((P, 3), **f32)
-    dsh = alloc((P, M, 3), **f32) if has_sh else torch.zeros((P, 0, 3), **f32)
-    dopacity = alloc((P, 1), **f32)
-    dscales = alloc((P, 3), **f32) if has_scales else None
-    drot = alloc((P, 4), **f32) if has_scales else None
+    if outputs is not None:
+        dmeans3D, dsh, dopacity, dscales, drot = outputs
+    else:
+        dmeans3D = alloc((P, 3), **f32)
+        dsh = alloc((P, M, 3), **f32) if has_sh else torch.zeros((P, 0, 3), **f32)
+        dopacity = alloc((P, 1), **f32)
+        dscales = alloc((P, 3), **f32) if has_scales else None
+        drot = alloc((P, 4), **f32) if has_scales else None
     dcolors = alloc((P, 3), **f32) if has_colors else None
     dcov = alloc((P, 6), **f32) if has_cov else None
     dview = alloc((F, 4, 4), **f32)
@@ -163,22 +173,34 @@ def _backward_batched(P, F, M, num_rendered, means3D, sh, colors_precomp, opacit
     if P == 0 or F == 0:
         return dmeans2D, dmeans3D, dsh, dopacity, dscales, drot, dcolors, dcov, dview, dproj, stats
     scratch = torch.empty(int(lib.dgs_blur_backward_scratch_bytes(P, F)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        rc = lib.dgs_blur_backward(
-            P, F, int(sh_degree), int(M), int(num_rendered),
-            _lib.ptr(bg), int(W), int(H),
-            _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors_precomp),
-            _lib.ptr(opacities), _lib.ptr(scales), float(scale_modifier),
-            _lib.ptr(rotations), _lib.ptr(cov3Ds_precomp),
-            _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos),
-            float(tanfovx), float(tanfovy), float(z_near), float(z_far), int(bool(use_sigmoid)),
-            _lib.ptr(radii), _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img),
-            _lib.ptr(grad_color), _lib.ptr(grad_depth), _lib.ptr(grad_blur), float(blur_denominator),
-            _lib.ptr(scratch),
-            _lib.ptr(dmeans2D), _lib.ptr(dmeans3D), _lib.ptr(dsh), _lib.ptr(dopacity),
-            _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
-            _lib.ptr(dview), _lib.ptr(dproj), _lib.ptr(stats), _stream_ptr(dev))
-    _lib.check(rc, "dgs_blur_backward")
+
+    def call(g0, g1, stages):
+        with torch.cuda.device(dev):
+            rc = lib.dgs_blur_backward_range(
+                P, F, int(sh_degree), int(M), int(num_rendered),
+                _lib.ptr(bg), int(W), int(H),
+                _lib.ptr(means3D), _lib.ptr(sh), _lib.ptr(colors_precomp),
+                _lib.ptr(opacities), _lib.ptr(scales), float(scale_modifier),
+                _lib.ptr(rotations), _lib.ptr(cov3Ds_precomp),
+                _lib.ptr(viewmatrix), _lib.ptr(projmatrix), _lib.ptr(campos),
+                float(tanfovx), float(tanfovy), float(z_near), float(z_far), int(bool(use_sigmoid)),
+                _lib.ptr(radii), _lib.ptr(geom), _lib.ptr(binning), _lib.ptr(img),
+                _lib.ptr(grad_color), _lib.ptr(grad_depth), _lib.ptr(grad_blur), float(blur_denominator),
+                _lib.ptr(scratch),
+                _lib.ptr(dmeans2D), _lib.ptr(dmeans3D), _lib.ptr(dsh), _lib.ptr(dopacity),
+                _lib.ptr(dscales), _lib.ptr(drot), _lib.ptr(dcolors), _lib.ptr(dcov),
+                _lib.ptr(dview), _lib.ptr(dproj), _lib.ptr(stats), int(g0), int(g1), int(stages), _stream_ptr(dev))
+        _lib.check(rc, "dgs_blur_backward_range")
+
+    if ranges is None:
+        call(0, P, BWD_ALL)
+    else:
+        call(0, 0, BWD_BLEND)
+        for (g0, g1) in ranges:
+            call(g0, g1, BWD_GAUSSIANS)
+            if on_range is not None:
+                on_range(g0, g1, (dmeans3D, dsh, dopacity, dscales, drot))
+        call(0, 0, BWD_FINISH)
     if _KEEP_SCRATCH:   # test hook: the per-(sub-frame, Gaussian) screen-space gradients the blend backward produced
         global _last_scratch
         _last_scratch = scratch
@@ -296,6 +318,112 @@ class _RasterizeBlurry(torch.autograd.Function):
             holder.fill(stats, ctx.denom)
         return (dmeans3D, dmeans2D, dsh if sh.numel() != 0 else None, dcolors, dopacity, dscales, drot, dcov,
                 dview, dproj, None, None, None, None)
+
+
+class _RenderStoreBlurry(torch.autograd.Function):
+    """Parameter store -> blurry view in one autograd node: the activations of the six raw parameter tensors
+    (dgs_activate_forward), the batched render, and a backward that finishes the Gaussians range by range -- the
+    per-Gaussian rasterizer backward and the activation chain rule of rows [g0, g1) -- so that a gradient sink
+    (dist.FlatGradBuffer) can start the NCCL all-reduce of those rows while the next range is computed.
+    With a sink the Gaussian gradients are WRITTEN into the sink's views (= the parameters' .grad) and this node
+    returns None for them; without one it returns them like any autograd node."""
+
+    @staticmethod
+    def forward(ctx, xyz, f_dc, f_rest, scaling, rotation, opacity, means2D, viewmatrix, projmatrix, campos,
+                raster_settings, blur_denominator, stats_holder, scale_lb, isotropic, grad_sink, n_ranges):
+        lib = _lib.load()
+        rs = raster_settings
+        _require_cuda(xyz, "xyz")
+        ctx.set_materialize_grads(False)
+        raw = [_f32c(t.detach()) for t in (xyz, f_dc, f_rest, scaling, rotation, opacity)]
+        xyz_c, dc_c, rest_c, sc_c, rot_c, op_c = raw
+        P = xyz_c.shape[0]
+        M = 1 + (rest_c.shape[1] if rest_c.dim() == 3 else 0)
+        dev = xyz_c.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        shs, scales = torch.empty((P, M, 3), **f32), torch.empty((P, 3), **f32)
+        rots, opac = torch.empty((P, 4), **f32), torch.empty((P, 1), **f32)
+        if P > 0:
+            with torch.cuda.device(dev):
+                rc = lib.dgs_activate_forward(P, M, _lib.ptr(dc_c), _lib.ptr(rest_c), _lib.ptr(sc_c), _lib.ptr(rot_c),
+                                              _lib.ptr(op_c), float(scale_lb), int(bool(isotropic)), _lib.ptr(shs),
+                                              _lib.ptr(scales), _lib.ptr(rots), _lib.ptr(opac), _stream_ptr(dev))
+            _lib.check(rc, "dgs_activate_forward")
+        view_c, proj_c, campos_c, bg_c = _f32c(viewmatrix), _f32c(projmatrix), _f32c(campos), _f32c(rs.bg)
+        F = view_c.shape[0]
+        denom = float(blur_denominator) if blur_denominator else float(F)
+        color, depth, radii, blur, num_rendered, geom, binning, img = _forward_batched(
+            xyz_c, shs, None, opac, scales, rots, None, view_c, proj_c, campos_c, bg_c, rs.image_height,
+            rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far, rs.sh_degree,
+            rs.prefiltered, rs.use_sigmoid, True, denom)
+        ctx.raster_settings, ctx.num_rendered, ctx.denom = rs, num_rendered, denom
+        ctx.want_means2D = means2D is not None and means2D.requires_grad
+        ctx.stats_holder, ctx.sink, ctx.n_ranges = stats_holder, grad_sink, max(1, int(n_ranges))
+        ctx.meta = (M, bool(isotropic), f_dc.shape, f_rest.shape)
+        ctx.save_for_backward(xyz_c, sc_c, rot_c, op_c, shs, scales, rots, opac, radii, geom, binning, img, view_c,
+                              proj_c, campos_c, bg_c)
+        ctx.mark_non_differentiable(radii)
+        return color, depth, radii, blur
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_depth, _radii, grad_blur):
+        lib = _lib.load()
+        rs = ctx.raster_settings
+        (xyz, sc, rot, op, shs, scales, rots, opac, radii, geom, binning, img, view, proj, campos, bg) = ctx.saved_tensors
+        M, isotropic, dc_shape, rest_shape = ctx.meta
+        P, F, dev = xyz.shape[0], view.shape[0], xyz.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        gc = _f32c(grad_color) if grad_color is not None else None
+        gb = _f32c(grad_blur) if grad_blur is not None else None
+        gd = _f32c(grad_depth) if grad_depth is not None else None
+        sink, holder = ctx.sink, ctx.stats_holder
+        if sink is not None:
+            v = sink.views
+            dxyz, ddc, drest, dsc, drot_raw, dop_raw = (v[k] for k in ("xyz", "f_dc", "f_rest", "scaling", "rotation", "opacity"))
+            sink.begin()
+        else:
+            dxyz, ddc, drest = torch.empty((P, 3), **f32), torch.empty(dc_shape, **f32), torch.empty(rest_shape, **f32)
+            dsc, drot_raw, dop_raw = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32), torch.empty((P, 1), **f32)
+        # activated-space gradients (inputs of the activation chain rule); dL/dxyz needs no chain rule
+        dsh, dopac = torch.empty((P, M, 3), **f32), torch.empty((P, 1), **f32)
+        dscales, drots = torch.empty((P, 3), **f32), torch.empty((P, 4), **f32)
+        n = ctx.n_ranges if P >= 4096 * ctx.n_ranges else 1
+        step = -(-P // n)
+        step = -(-step // 128) * 128                 # ranges start on a block boundary (keeps 16-B aligned rows)
+        ranges = [(g0, min(P, g0 + step)) for g0 in range(0, P, step)] if P > 0 else []
+        st = _stream_ptr(dev)
+
+        def after_range(g0, g1, _out):
+            rows = g1 - g0
+            o = lambda t, w: t.data_ptr() + g0 * w * 4
+            with torch.cuda.device(dev):
+                rc = lib.dgs_activate_backward(
+                    rows, M, o(sc, 3), o(rot, 4), o(op, 1), int(isotropic), o(dsh, 3 * M), o(dscales, 3), o(drots, 4),
+                    o(dopac, 1), o(ddc, 3), o(drest, 3 * (M - 1)) if M > 1 else None, o(dsc, 3), o(drot_raw, 4),
+                    o(dop_raw, 1), st)
+            _lib.check(rc, "dgs_activate_backward")
+            if sink is not None:
+                sink.rows_done(g0, g1)
+
+        (dmeans2D, _, _, _, _, _, _, _, dview, dproj, stats) = _backward_batched(
+            P, F, M, ctx.num_rendered, xyz, shs, None, opac, scales, rots, None, view, proj, campos, bg,
+            rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier, rs.z_near, rs.z_far,
+            rs.sh_degree, rs.use_sigmoid, radii, geom, binning, img, gc, gd, ctx.want_means2D, gb, ctx.denom,
+            holder is not None, ranges=ranges, outputs=(dxyz, dsh, dopac, dscales, drots), on_range=after_range)
+        if holder is not None:
+            holder.fill(stats, ctx.denom)
+        if sink is not None:
+            sink.finish()
+            return (None, None, None, None, None, None, dmeans2D, dview, dproj) + (None,) * 8
+        return (dxyz, ddc, drest, dsc, drot_raw, dop_raw, dmeans2D, dview, dproj) + (None,) * 8
+
+
+def render_store_blurry(xyz, features_dc, features_rest, scaling, rotation, opacity, means2D, viewmatrix, projmatrix,
+                        campos, raster_settings, blur_denominator=None, stats_holder=None, scale_lower_bound=0.0,
+                        isotropic=False, grad_sink=None, n_ranges=4):
+    return _RenderStoreBlurry.apply(xyz, features_dc, features_rest, scaling, rotation, opacity, means2D, viewmatrix,
+                                    projmatrix, campos, raster_settings, blur_denominator, stats_holder,
+                                    scale_lower_bound, isotropic, grad_sink, n_ranges)
 
 
 class DensificationStats:

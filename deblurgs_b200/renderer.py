@@ -9,7 +9,7 @@ import math
 import torch
 
 from .rasterizer import (DensificationStats, GaussianRasterizationSettings, GaussianRasterizer,
-                         rasterize_blurry)
+                         rasterize_blurry, render_store_blurry)
 
 
 def render(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, override_color=None, *_compat):
@@ -76,7 +76,7 @@ def render(viewpoint_camera, pc, bg_color, scaling_modifier=1.0, override_color=
 
 
 def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, ref_cam, pc, bg_color,
-                  scaling_modifier=1.0, override_color=None, blur_denominator=None):
+                  scaling_modifier=1.0, override_color=None, blur_denominator=None, grad_sink=None):
     """Render all F sub-frames of a blurry view in one batched call.
 
     world_view_transforms / full_proj_transforms [F,4,4], camera_centers [F,3]: the MiniCam tensors of
@@ -106,6 +106,17 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
         prefiltered=False,
         debug=False,
     )
+    stats = DensificationStats()   # filled by the backward pass
+    sink = grad_sink if grad_sink is not None else getattr(pc, "grad_sink", None)
+    if sink is not None and override_color is None and hasattr(pc, "_features_rest"):
+        # parameter store + gradient sink (dist.FlatGradBuffer): activations, render and a range-by-range backward in one
+        # autograd node, so that the all-reduce of finished rows overlaps the rest of the backward
+        color, depth, radii, blurred = render_store_blurry(
+            pc._xyz, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation, pc._opacity, screenspace_points,
+            world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator, stats,
+            getattr(pc, "scale_lower_bound", 0.0), getattr(pc, "use_isotropic", False), sink)
+        return {"render": color, "depth": depth, "blurred": blurred, "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0, "radii": radii, "densification": stats}
     if hasattr(pc, "get_activated"):
         # parameter store with the fused activation kernel (params.activate_gaussians): one launch
         shs, scales, rotations, opacities = pc.get_activated()
@@ -114,7 +125,6 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
         shs, scales, rotations, opacities = pc.get_features, pc.get_scaling, pc.get_rotation, pc.get_opacity
     if override_color is not None:
         shs = None
-    stats = DensificationStats()   # filled by the backward pass
     color, depth, radii, blurred = rasterize_blurry(
         xyz, screenspace_points, shs, override_color, opacities, scales, rotations, None,
         world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator, stats)

@@ -155,6 +155,37 @@ int dgs_blur_backward(
     float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
     float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats, void* stream);
 
+/*
+ * The batched backward in pieces, so that a caller can overlap a collective with it: `stages` is a bit set of
+ *   DGS_BWD_BLEND      scratch clear + tile-blend backward (all sub-frames)
+ *   DGS_BWD_GAUSSIANS  per-Gaussian backward for the Gaussians [g_begin, g_end): their rows of every Gaussian
+ *                      gradient (and of dL_dmeans2D / densify_stats) are final when it completes, so e.g. an NCCL
+ *                      all-reduce of those rows can run while the next range is computed
+ *   DGS_BWD_FINISH     view / projection-matrix gradients (accumulated over all ranges) -> dL_dviewmatrix / dL_dprojmatrix
+ * Call BLEND once, GAUSSIANS for ranges that cover [0, P) in any order, FINISH last, all with the same arguments
+ * and scratch on the same stream.  dgs_blur_backward = all three over [0, P).
+ */
+#define DGS_BWD_BLEND 1
+#define DGS_BWD_GAUSSIANS 2
+#define DGS_BWD_FINISH 4
+#define DGS_BWD_ALL 7
+int dgs_blur_backward_range(
+    int P, int F, int sh_degree, int sh_coeffs, int64_t num_rendered,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* campos,
+    float tan_fovx, float tan_fovy, float z_near, float z_far, int use_sigmoid,
+    const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpixdepth, const float* dL_dblur, float blur_denominator,
+    char* scratch,
+    float* dL_dmeans2D, float* dL_dmeans3D, float* dL_dsh, float* dL_dopacity,
+    float* dL_dscales, float* dL_drotations, float* dL_dcolors_precomp, float* dL_dcov3D_precomp,
+    float* dL_dviewmatrix, float* dL_dprojmatrix, float* densify_stats,
+    int64_t g_begin, int64_t g_end, int stages, void* stream);
+
 /* Single-view pair: the reference's rasterize_gaussians / rasterize_gaussians_backward
  * (same argument meaning; F = 1 instance of the batched pair). */
 int dgs_forward(
