@@ -342,11 +342,7 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_render_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
-        configured = true;
-    }
+    static_assert(sizeof(BwdSmem) <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device opt-in needed");
     dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
     k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p);
 }
@@ -450,53 +446,62 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
             const float ddepth = gb.z;
             float3 dcol = {gc.x, gc.y, gc.z};
 
-            // ---- cov2D / EWA backward (reference backward.cu:145-295)
+            // ---- EWA projection backward (what the reference's computeCov2DCUDA backward computes, backward.cu:145-295),
+            // derived here from the matrix identities instead of the expanded scalar formulas:
+            //   Sigma2 = [[a, b], [b, c]] = (J Mv) Sigma3 (J Mv)^T + 0.3 I,   K = Sigma2^-1 = the conic.
+            //   The blend backward delivers Gm = dL/dK as a full symmetric matrix ((x, y; y, w): the off-diagonal
+            //   entry counted once per position).  d(K) = -K d(Sigma2) K  =>  dL/dSigma2 = -K Gm K, and b occupies both
+            //   off-diagonal positions, so dL/db is twice that entry.
             const Ewa e = ewa_project(mean, f.focal_x, f.focal_y, f.tan_fovx, f.tan_fovy, cov3D, V);
-            const float limx = 1.3f * f.tan_fovx, limy = 1.3f * f.tan_fovy;
-            const float x_grad_mul = (e.txtz < -limx || e.txtz > limx) ? 0.f : 1.f;
-            const float y_grad_mul = (e.tytz < -limy || e.tytz > limy) ? 0.f : 1.f;
-            const float a = e.a, b = e.b, c = e.c;
-            const float denom = a * c - b * b;
-            float dL_da = 0, dL_db = 0, dL_dc = 0;
-            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-            const Mat3& T = e.T;
-            if (denom2inv != 0) {
-                dL_da = denom2inv * (-c * c * dconic.x + 2 * b * c * dconic.y + (denom - a * c) * dconic.z);
-                dL_dc = denom2inv * (-a * a * dconic.z + 2 * a * b * dconic.y + (denom - a * c) * dconic.x);
-                dL_db = denom2inv * 2 * (b * c * dconic.x - (denom + 2 * b * b) * dconic.y + a * b * dconic.z);
-                dcov[0] += (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-                dcov[3] += (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-                dcov[5] += (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-                dcov[1] += 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-                dcov[2] += 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-                dcov[4] += 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+            const float inv_det = 1.0f / (e.a * e.c - e.b * e.b);        // Sigma2 >= 0.3 I: never singular
+            const float k00 = e.c * inv_det, k01 = -e.b * inv_det, k11 = e.a * inv_det;
+            const float kg00 = k00 * dconic.x + k01 * dconic.y, kg01 = k00 * dconic.y + k01 * dconic.z;   // K Gm, row 0
+            const float kg10 = k01 * dconic.x + k11 * dconic.y, kg11 = k01 * dconic.y + k11 * dconic.z;   //       row 1
+            const float da = -(kg00 * k00 + kg01 * k01);
+            const float dc = -(kg10 * k01 + kg11 * k11);
+            const float db = -2.0f * (kg00 * k01 + kg01 * k11);
+            //   With u, v the two rows of J Mv (the Ewa struct keeps them as T.m[0][.], T.m[1][.]):
+            //   a = u.S3.u, b = u.S3.v, c = v.S3.v.  Gradient w.r.t. the six stored entries of the symmetric Sigma3
+            //   (an off-diagonal entry stands for two positions, hence the doubled terms there):
+            const float u[3] = {e.T.m[0][0], e.T.m[0][1], e.T.m[0][2]};
+            const float v[3] = {e.T.m[1][0], e.T.m[1][1], e.T.m[1][2]};
+            {
+                constexpr int slot[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = i; j < 3; j++) {
+                        const float g = u[i] * u[j] * da + 0.5f * (u[i] * v[j] + u[j] * v[i]) * db + v[i] * v[j] * dc;
+                        dcov[slot[i][j]] += (i == j) ? g : 2.0f * g;
+                    }
             }
-            // Vrk (symmetric)
-            const float V00 = cov3D[0], V01 = cov3D[1], V02 = cov3D[2], V11 = cov3D[3], V12 = cov3D[4], V22 = cov3D[5];
-            const float r0x = T.m[0][0] * V00 + T.m[0][1] * V01 + T.m[0][2] * V02;
-            const float r0y = T.m[0][0] * V01 + T.m[0][1] * V11 + T.m[0][2] * V12;
-            const float r0z = T.m[0][0] * V02 + T.m[0][1] * V12 + T.m[0][2] * V22;
-            const float r1x = T.m[1][0] * V00 + T.m[1][1] * V01 + T.m[1][2] * V02;
-            const float r1y = T.m[1][0] * V01 + T.m[1][1] * V11 + T.m[1][2] * V12;
-            const float r1z = T.m[1][0] * V02 + T.m[1][1] * V12 + T.m[1][2] * V22;
-            const float dL_dT00 = 2 * r0x * dL_da + r1x * dL_db;
-            const float dL_dT01 = 2 * r0y * dL_da + r1y * dL_db;
-            const float dL_dT02 = 2 * r0z * dL_da + r1z * dL_db;
-            const float dL_dT10 = 2 * r1x * dL_dc + r0x * dL_db;
-            const float dL_dT11 = 2 * r1y * dL_dc + r0y * dL_db;
-            const float dL_dT12 = 2 * r1z * dL_dc + r0z * dL_db;
-            const Mat3& W = e.W;
-            const float dL_dJ00 = W.m[0][0] * dL_dT00 + W.m[0][1] * dL_dT01 + W.m[0][2] * dL_dT02;
-            const float dL_dJ02 = W.m[2][0] * dL_dT00 + W.m[2][1] * dL_dT01 + W.m[2][2] * dL_dT02;
-            const float dL_dJ11 = W.m[1][0] * dL_dT10 + W.m[1][1] * dL_dT11 + W.m[1][2] * dL_dT12;
-            const float dL_dJ12 = W.m[2][0] * dL_dT10 + W.m[2][1] * dL_dT11 + W.m[2][2] * dL_dT12;
-            const float tz = 1.f / e.t.z;
-            const float tz2 = tz * tz;
-            const float tz3 = tz2 * tz;
-            const float hx = f.focal_x, hy = f.focal_y;
-            const float dL_dtx = x_grad_mul * -hx * tz2 * dL_dJ02;
-            const float dL_dty = y_grad_mul * -hy * tz2 * dL_dJ12;
-            const float dL_dtz = -hx * tz2 * dL_dJ00 - hy * tz2 * dL_dJ11 + (2 * hx * e.t.x) * tz3 * dL_dJ02 + (2 * hy * e.t.y) * tz3 * dL_dJ12;
+            //   Gradient w.r.t. the rows themselves: du = 2 da S3 u + db S3 v,  dv = 2 dc S3 v + db S3 u.
+            const float S3[3][3] = {{cov3D[0], cov3D[1], cov3D[2]}, {cov3D[1], cov3D[3], cov3D[4]}, {cov3D[2], cov3D[4], cov3D[5]}};
+            float du[3], dv[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float su = S3[i][0] * u[0] + S3[i][1] * u[1] + S3[i][2] * u[2];
+                const float sv = S3[i][0] * v[0] + S3[i][1] * v[1] + S3[i][2] * v[2];
+                du[i] = 2.0f * da * su + db * sv;
+                dv[i] = 2.0f * dc * sv + db * su;
+            }
+            //   u = j00 Mv[0] + j02 Mv[2],  v = j11 Mv[1] + j12 Mv[2]  with the perspective Jacobian
+            //   j00 = fx / tz, j02 = -fx tx / tz^2, j11 = fy / tz, j12 = -fy ty / tz^2  (Mv rows = e.W.m[k][.]).
+            const Mat3& Mv = e.W;
+            const float d_j00 = du[0] * Mv.m[0][0] + du[1] * Mv.m[0][1] + du[2] * Mv.m[0][2];
+            const float d_j02 = du[0] * Mv.m[2][0] + du[1] * Mv.m[2][1] + du[2] * Mv.m[2][2];
+            const float d_j11 = dv[0] * Mv.m[1][0] + dv[1] * Mv.m[1][1] + dv[2] * Mv.m[1][2];
+            const float d_j12 = dv[0] * Mv.m[2][0] + dv[1] * Mv.m[2][1] + dv[2] * Mv.m[2][2];
+            //   ... and the Jacobian entries depend on the (clamped) view-space mean t: with iz = 1 / tz,
+            //   kx = -fx iz^2, ky = -fy iz^2:  d j02/d tx = kx,  d j00/d tz = kx,  d j02/d tz = -2 iz kx tx  (same in y).
+            //   Where the forward clamped tx/tz (ty/tz) to the frustum guard band, t no longer follows the mean.
+            const float limx = 1.3f * f.tan_fovx, limy = 1.3f * f.tan_fovy;
+            const bool free_x = !(e.txtz < -limx || e.txtz > limx), free_y = !(e.tytz < -limy || e.tytz > limy);
+            const float iz = 1.0f / e.t.z;
+            const float kx = -f.focal_x * iz * iz, ky = -f.focal_y * iz * iz;
+            const float dL_dtx = free_x ? kx * d_j02 : 0.f;
+            const float dL_dty = free_y ? ky * d_j12 : 0.f;
+            const float dL_dtz = kx * d_j00 + ky * d_j11 - 2.0f * iz * (kx * e.t.x * d_j02 + ky * e.t.y * d_j12);
             // dL/dmean through t (V^T applied to the 3-vector)
             float3 dm;
             dm.x = V[0] * dL_dtx + V[1] * dL_dty + V[2] * dL_dtz;
@@ -551,43 +556,41 @@ __global__ void __launch_bounds__(PRE_BWD_THREADS) k_preprocess_bwd(const BwdPar
             for (int i = 0; i < 6; i++) p.dL_dcov3D_precomp[6 * (size_t)g + i] = dcov[i];
         }
     } else {
-        // cov3D -> scale / rotation (reference backward.cu:299-362); linear in dL/dcov3D, so
-        // it is applied once to the sum over sub-frames.
+        // Sigma3 -> scale / rotation (what the reference's computeCov3D backward computes, backward.cu:299-362);
+        // linear in dL/dSigma3, so it is applied once to the sum over the sub-frames.  Derivation:
+        //   Sigma3 = Rq S^2 Rq^T,  Rq = rotation of the (un-normalised) quaternion, S = diag(mod * scale).
+        //   D = dL/dSigma3 as a full symmetric matrix (stored off-diagonal entries stand for two positions: halve them).
+        //   H = 2 D Rq;  dL/dRq = H S^2;  dL/ds_j = s_j sum_i Rq_ij H_ij  (the reference differentiates w.r.t.
+        //   s = mod * scale and reports that as the scale gradient; reproduced).
         const float r = q.x, x = q.y, y = q.z, z = q.w;
-        Mat3 R;
-        R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
-        R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-        R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-        const float3 sv = {f.scale_modifier * scale.x, f.scale_modifier * scale.y, f.scale_modifier * scale.z};
-        Mat3 S;
+        const float Rq[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+        const float D[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                               {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                               {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+        const float sv[3] = {f.scale_modifier * scale.x, f.scale_modifier * scale.y, f.scale_modifier * scale.z};
+        float G[3][3];      // dL/dRq
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int j = 0; j < 3; j++) {
+            float ds = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 3; rr++) S.m[c][rr] = 0.f;
-        S.m[0][0] = sv.x; S.m[1][1] = sv.y; S.m[2][2] = sv.z;
-        const Mat3 Mm = mat3_mul(S, R);
-        Mat3 dSigma;
-        dSigma.m[0][0] = dcov[0];        dSigma.m[0][1] = 0.5f * dcov[1]; dSigma.m[0][2] = 0.5f * dcov[2];
-        dSigma.m[1][0] = 0.5f * dcov[1]; dSigma.m[1][1] = dcov[3];        dSigma.m[1][2] = 0.5f * dcov[4];
-        dSigma.m[2][0] = 0.5f * dcov[2]; dSigma.m[2][1] = 0.5f * dcov[4]; dSigma.m[2][2] = dcov[5];
-        Mat3 M2;
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) M2.m[c][rr] = 2.0f * Mm.m[c][rr];
-        const Mat3 dL_dM = mat3_mul(M2, dSigma);
-        const Mat3 Rt = mat3_transpose(R);
-        Mat3 dMt = mat3_transpose(dL_dM);
-        p.dL_dscales[3 * g]     = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-        p.dL_dscales[3 * g + 1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-        p.dL_dscales[3 * g + 2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-        for (int rr = 0; rr < 3; rr++) { dMt.m[0][rr] *= sv.x; dMt.m[1][rr] *= sv.y; dMt.m[2][rr] *= sv.z; }
+            for (int i = 0; i < 3; i++) {
+                const float h = 2.0f * (D[i][0] * Rq[0][j] + D[i][1] * Rq[1][j] + D[i][2] * Rq[2][j]);
+                ds += Rq[i][j] * h;
+                G[i][j] = h * sv[j] * sv[j];
+            }
+            p.dL_dscales[3 * g + j] = sv[j] * ds;
+        }
+        // Rq is linear in the products of quaternion components; split G into its antisymmetric part (an axial
+        // vector w, which pairs with r) and its symmetric part (which pairs with x, y, z):
+        const float wx = G[2][1] - G[1][2], wy = G[0][2] - G[2][0], wz = G[1][0] - G[0][1];
+        const float sxy = G[0][1] + G[1][0], sxz = G[0][2] + G[2][0], syz = G[1][2] + G[2][1];
         float4 dq;
-        dq.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
-        dq.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
-        dq.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
-        dq.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        dq.x = 2.f * (x * wx + y * wy + z * wz);
+        dq.y = 2.f * (r * wx + y * sxy + z * sxz) - 4.f * x * (G[1][1] + G[2][2]);
+        dq.z = 2.f * (r * wy + x * sxy + z * syz) - 4.f * y * (G[0][0] + G[2][2]);
+        dq.w = 2.f * (r * wz + x * sxz + y * syz) - 4.f * z * (G[0][0] + G[1][1]);
         reinterpret_cast<float4*>(p.dL_drotations)[g] = dq;
     }
 }
