@@ -402,7 +402,10 @@ def other_config(name, rank, world, device, steps=3, warmup=3):
     scaling: value = views/s of that one view); c4 = one 3 M-Gaussian view per rank (weak: value = world x views/s)."""
     strong = name == "c3"
     w = build_workload(name, 0 if strong else rank, device)
-    step = make_step_subframe_sharded(w, world) if (strong and world > 1) else make_step_ours(w, 1 if strong else world)
+    if name == "c1":      # BASELINE config 1 (the CPU-runnable case): launch-bound kernel by kernel, so replayed as a graph
+        step = make_step_ours(w, 1, 0.0, True)
+    else:
+        step = make_step_subframe_sharded(w, world) if (strong and world > 1) else make_step_ours(w, 1 if strong else world)
     mode = ("subframes-sharded-%d (NCCL all-reduce of the blurred image; gradient all-reduce overlapped with the backward)"
             % world) if (strong and world > 1) else None
     gt = w["gt_host"].to(device)
@@ -411,10 +414,12 @@ def other_config(name, rank, world, device, steps=3, warmup=3):
     ms = time_steps(step, gt, steps, world, device)
     loss = float(step(gt).item())
     P, W, H, F = w["P"], w["W"], w["H"], w["F"]
+    mode_str = getattr(step, "mode", "kernel by kernel")
     del w, step
     torch.cuda.empty_cache()
     return {"workload": "%s: %d Gaussians, %dx%d, num_subframes=%d" % (name, P, W, H, F),
-            "parallelism": mode if mode else ("single GPU" if strong else "views-dp%d" % world),
+            "parallelism": mode if mode else ("single GPU" if (strong or name == "c1") else "views-dp%d" % world),
+            "launch_mode": mode_str,
             "scaling": "strong" if strong else "weak", "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "value": (1.0 if strong else world) * 1000.0 / ms, "unit": UNIT, "loss_last": loss}
 
@@ -542,7 +547,7 @@ def main():
     others = None
     if args.impl == "ours" and not args.no_other_configs and args.config == "c2" and not sharded:
         others = {}
-        for name in ("c3", "c4"):
+        for name in (("c1",) if eff_world == 1 else ()) + ("c3", "c4"):
             try:
                 others[name] = other_config(name, rank, eff_world, device)
             except Exception as e:   # never lose the headline line to an out-of-memory on the big shapes
