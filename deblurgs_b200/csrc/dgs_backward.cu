@@ -101,7 +101,7 @@ struct HalvingReduce {
 // ---------------------------------------------------------------------------------------
 #define BWD_WARPS 4               // warps per block: a block owns a 16 x (4*BWD_WARPS/2) strip of a tile
 #define BWD_THREADS (32 * BWD_WARPS)
-#define BWD_QN 16                 // queued entries per flush
+#define BWD_QN 8                  // queued entries per flush
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
 
 struct BwdSmem {
@@ -116,9 +116,10 @@ struct BwdSmem {
     int tile_max;
 };
 
-// Phase 2.  Lane (e, half) owns queued entry e and the 16 pixels of rows 2*half, 2*half+1 of the warp's
-// 8x4 rectangle.  The weighted moments are accumulated about the rectangle's corner with the pixel
-// offsets as compile-time constants (sum w, sum w*px, sum w*px^2, ...; py is 0 or 1), and shifted to the
+// Phase 2.  Lane (e, quarter) owns queued entry e and the 8 pixels of row `quarter` of the warp's 8x4
+// rectangle (8 queued entries x 4 rows = 32 busy lanes; the queue is half the size of a 16-entry one, which is what
+// bounds the resident warps per SM).  The weighted moments are accumulated about the row's first pixel with the
+// pixel offsets as compile-time constants (sum w, sum w*px, sum w*px^2), and shifted to the
 // Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
 // until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the staging
 // pass fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
@@ -128,7 +129,7 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
                                           float4* __restrict__ gp0, float4* __restrict__ gp1, float4* __restrict__ gp2)
 {
     __syncwarp();
-    const unsigned e = lane & 15u, half = lane >> 4;
+    const unsigned e = lane & 7u, quarter = lane >> 3;     // queued entry, pixel row of the warp's 8x4 rectangle
     const bool live = (int)e < qn;
     uint32_t id = 0;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
@@ -137,32 +138,34 @@ __device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned l
         g0 = __ldg(geo0 + id);   // x, y, depth, radius
         g1 = __ldg(geo1 + id);   // conic a, b, c, opacity
     }
-    float M0 = 0.f, Mx = 0.f, My = 0.f, Mxx = 0.f, Mxy = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
+    float M0 = 0.f, Mx = 0.f, Mxx = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
 #pragma unroll
-    for (int pp = 0; pp < 16; pp++) {
-        const float2 w = sm.qw[warp][e][half * 16 + pp];
-        const float4 dp = sm.dpix[warp][half * 16 + pp];
-        const float px = (float)(pp & 7);
+    for (int pp = 0; pp < 8; pp++) {
+        const float2 w = sm.qw[warp][e][quarter * 8 + pp];
+        const float4 dp = sm.dpix[warp][quarter * 8 + pp];
+        const float px = (float)pp;
         M0 += w.x;
         Mx = fmaf(w.x, px, Mx);
         Mxx = fmaf(w.x, px * px, Mxx);
-        if (pp >= 8) { My += w.x; Mxy = fmaf(w.x, px, Mxy); }   // py = 1 (py^2 = py: Myy = My)
         Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
     }
-    // shift to the centre: pixel (px, py) of this half is at distance (bx - px, by - py) from it
-    const float bx = g0.x - wx0f, by = g0.y - (wy0f + 2.0f * (float)half);
+    // shift to the centre: pixel px of this row is at distance (bx - px, by) from it
+    const float bx = g0.x - wx0f, by = g0.y - (wy0f + (float)quarter);
     float S0 = M0;
     float Sx = bx * M0 - Mx;
-    float Sy = by * M0 - My;
+    float Sy = by * M0;
     float Sxx = bx * (bx * M0 - 2.0f * Mx) + Mxx;
-    float Sxy = bx * (by * M0 - My) - by * Mx + Mxy;
-    float Syy = by * (by * M0 - 2.0f * My) + My;
-    S0 += __shfl_xor_sync(FULL_MASK, S0, 16);   Sx += __shfl_xor_sync(FULL_MASK, Sx, 16);
-    Sy += __shfl_xor_sync(FULL_MASK, Sy, 16);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, 16);
-    Sxy += __shfl_xor_sync(FULL_MASK, Sxy, 16); Syy += __shfl_xor_sync(FULL_MASK, Syy, 16);
-    Cr += __shfl_xor_sync(FULL_MASK, Cr, 16);   Cg += __shfl_xor_sync(FULL_MASK, Cg, 16);
-    Cb += __shfl_xor_sync(FULL_MASK, Cb, 16);   Cd += __shfl_xor_sync(FULL_MASK, Cd, 16);
-    if (half == 0 && live) {
+    float Sxy = by * Sx;
+    float Syy = by * Sy;
+#pragma unroll
+    for (int d = 8; d <= 16; d <<= 1) {      // sum the four rows
+        S0 += __shfl_xor_sync(FULL_MASK, S0, d);   Sx += __shfl_xor_sync(FULL_MASK, Sx, d);
+        Sy += __shfl_xor_sync(FULL_MASK, Sy, d);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, d);
+        Sxy += __shfl_xor_sync(FULL_MASK, Sxy, d); Syy += __shfl_xor_sync(FULL_MASK, Syy, d);
+        Cr += __shfl_xor_sync(FULL_MASK, Cr, d);   Cg += __shfl_xor_sync(FULL_MASK, Cg, d);
+        Cb += __shfl_xor_sync(FULL_MASK, Cb, d);   Cd += __shfl_xor_sync(FULL_MASK, Cd, d);
+    }
+    if (quarter == 0 && live) {
         const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
         // three 16-B vector reductions (sm_90+ red.global.add.v4.f32), one per gradient plane, instead of ten scalar ones
         red_add_v4(reinterpret_cast<float*>(gp0 + id), -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy,
