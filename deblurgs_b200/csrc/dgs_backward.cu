@@ -103,13 +103,14 @@ struct HalvingReduce {
 #define BWD_THREADS (32 * BWD_WARPS)
 #define BWD_QN 8                  // queued entries per flush
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
+#define BWD_BATCH 256             // list entries staged per round
 
 struct BwdSmem {
-    uint8_t wm[DGS_TILE_PIX];            // which warps of the tile blended the staged entry (written by the forward)
-    uint32_t id[DGS_TILE_PIX];           // Gaussian index of the staged entry
-    float2 xy[DGS_TILE_PIX];
-    float4 con[DGS_TILE_PIX];
-    float4 rgbd[DGS_TILE_PIX];
+    uint8_t wm[BWD_BATCH];            // which warps of the tile blended the staged entry (written by the forward)
+    uint32_t id[BWD_BATCH];           // Gaussian index of the staged entry
+    float2 xy[BWD_BATCH];
+    float4 con[BWD_BATCH];
+    float4 rgbd[BWD_BATCH];
     float2 qw[BWD_WARPS][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
     uint32_t qid[BWD_WARPS][BWD_QN];             // per warp: Gaussian index of the queued entry
     float4 dpix[BWD_WARPS][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
@@ -258,16 +259,16 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
     float R = T_final * bg_dot_dpixel;
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
 
-    const int rounds = (list_len + DGS_TILE_PIX - 1) / DGS_TILE_PIX;
+    const int rounds = (list_len + BWD_BATCH - 1) / BWD_BATCH;
     int todo = list_len;
     int qn = 0;   // queued entries of this warp (warp-uniform)
 
-    for (int i = 0; i < rounds; i++, todo -= DGS_TILE_PIX) {
+    for (int i = 0; i < rounds; i++, todo -= BWD_BATCH) {
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < DGS_TILE_PIX / BWD_THREADS; k++) {
+        for (int k = 0; k < BWD_BATCH / BWD_THREADS; k++) {
             const int slot = k * BWD_THREADS + tid;
-            const int progress = i * DGS_TILE_PIX + slot;
+            const int progress = i * BWD_BATCH + slot;
             if (progress < list_len) {
                 const uint32_t lp = range.x + list_len - progress - 1;
                 const uint32_t id = p.point_list[lp];
@@ -281,9 +282,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
             }
         }
         __syncthreads();
-        const int batch = min(DGS_TILE_PIX, todo);
+        const int batch = min(BWD_BATCH, todo);
         // entry j of this batch sits at list position first_pos - j (the batch is staged back to front)
-        const int first_pos = list_len - i * DGS_TILE_PIX - 1;
+        const int first_pos = list_len - i * BWD_BATCH - 1;
         for (int c0 = 0; c0 < batch; c0 += 32) {
             const int jl = c0 + (int)lane;
             // the forward recorded which (warp, entry) pairs blended at least one pixel: visit exactly those
