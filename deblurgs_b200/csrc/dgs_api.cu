@@ -526,6 +526,7 @@ int dgs_blur_backward_range(
     if (!geom_buffer || !binning_buffer || !image_buffer || !scratch || !radii)
         return fail(DGS_ERR_INVALID_ARGUMENT, "null state buffer");
     if (!dL_dmeans3D || !dL_dopacity) return fail(DGS_ERR_INVALID_ARGUMENT, "null gradient output");
+    if (P >= (1 << 27)) return fail(DGS_ERR_UNSUPPORTED, "the blend backward packs the Gaussian index into 27 bits: P must be < 2^27");
     if (shs && !dL_dsh) return fail(DGS_ERR_INVALID_ARGUMENT, "null dL_dsh");
     if (scales && (!dL_dscales || !dL_drotations)) return fail(DGS_ERR_INVALID_ARGUMENT, "null dL_dscales/dL_drotations");
 

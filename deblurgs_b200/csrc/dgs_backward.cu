@@ -21,6 +21,7 @@
 // (21 values per sub-frame) are reduced over the warp with a 23-shuffle halving exchange (each
 // step trades half of the remaining components with the partner lane) and accumulated in fp64.
 #include "dgs_internal.cuh"
+#include <cstdlib>
 
 namespace dgs {
 
@@ -342,13 +343,263 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
     if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-independent variant (round 2, second half).  The forward's hand-over byte says exactly which list entries a
+// warp blended, so a warp no longer needs the block's staged copy of the WHOLE tile list: it reads 32 hand-over bytes
+// + list ids per step (coalesced), and only the lanes whose entry it blended gather that entry's three 16-B records --
+// straight into the warp's own shared-memory slots with cp.async (no registers, no block barrier), compacted back to
+// front.  The gather of step k+1 and the byte / id loads of step k+2 are in flight while step k is replayed.  Nothing
+// is shared between warps any more: no __syncthreads, no strip-wide replay depth (each warp starts at ITS deepest
+// contributor), and ~8x fewer gathered records than staging every entry for every strip.
+// ---------------------------------------------------------------------------------------
+struct __align__(16) BwdWarpSmem {
+    float4 rec[2][32][3];                 // [buffer][compacted entry] -> geo0 | geo1 | geo2 records (cp.async targets)
+    uint32_t idr[2][32];                  // Gaussian index | (list position relative to the step's lowest) << 27
+    float2 qw[BWD_QN][BWD_QSTRIDE];       // [queued entry][pixel] -> (w1, w2)
+    float4 dpix[32];                      // dL/dpix r,g,b,depth of the warp's 32 pixels
+    uint32_t qid[BWD_QN];                 // Gaussian index of the queued entry
+};
+#define BWD_ID_BITS 27
+#define BWD_ID_MASK ((1u << BWD_ID_BITS) - 1u)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// Phase 2 of the warp-independent kernel: same arithmetic as bwd_flush above, on the warp's own queue.
+__device__ __forceinline__ void bwd_flush_w(BwdWarpSmem& sm, unsigned lane, int qn, float wx0f, float wy0f,
+                                            float ddelx_dx, float ddely_dy, const float4* __restrict__ geo0,
+                                            const float4* __restrict__ geo1, float4* __restrict__ gp0,
+                                            float4* __restrict__ gp1, float4* __restrict__ gp2)
+{
+    __syncwarp();
+    const unsigned e = lane & 7u, quarter = lane >> 3;
+    const bool live = (int)e < qn;
+    uint32_t id = 0;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    if (live) {
+        id = sm.qid[e];
+        g0 = __ldg(geo0 + id);
+        g1 = __ldg(geo1 + id);
+    }
+    float M0 = 0.f, Mx = 0.f, Mxx = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 8; pp++) {
+        const float2 w = sm.qw[e][quarter * 8 + pp];
+        const float4 dp = sm.dpix[quarter * 8 + pp];
+        const float px = (float)pp;
+        M0 += w.x;
+        Mx = fmaf(w.x, px, Mx);
+        Mxx = fmaf(w.x, px * px, Mxx);
+        Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
+    }
+    const float bx = g0.x - wx0f, by = g0.y - (wy0f + (float)quarter);
+    float S0 = M0;
+    float Sx = bx * M0 - Mx;
+    float Sy = by * M0;
+    float Sxx = bx * (bx * M0 - 2.0f * Mx) + Mxx;
+    float Sxy = by * Sx;
+    float Syy = by * Sy;
+#pragma unroll
+    for (int d = 8; d <= 16; d <<= 1) {
+        S0 += __shfl_xor_sync(FULL_MASK, S0, d);   Sx += __shfl_xor_sync(FULL_MASK, Sx, d);
+        Sy += __shfl_xor_sync(FULL_MASK, Sy, d);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, d);
+        Sxy += __shfl_xor_sync(FULL_MASK, Sxy, d); Syy += __shfl_xor_sync(FULL_MASK, Syy, d);
+        Cr += __shfl_xor_sync(FULL_MASK, Cr, d);   Cg += __shfl_xor_sync(FULL_MASK, Cg, d);
+        Cb += __shfl_xor_sync(FULL_MASK, Cb, d);   Cd += __shfl_xor_sync(FULL_MASK, Cd, d);
+    }
+    if (quarter == 0 && live) {
+        const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
+        red_add_v4(reinterpret_cast<float*>(gp0 + id), -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy,
+                   -0.5f * Sxx, -0.5f * Sxy);
+        red_add_v4(reinterpret_cast<float*>(gp1 + id), -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, 0.f);
+        red_add_v4(reinterpret_cast<float*>(gp2 + id), Cr, Cg, Cb, 0.f);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FwdParams& f = p.f;
+    const int s = blockIdx.z;
+    constexpr unsigned BWD_STRIPS = 8 / BWD_WARPS, STRIP_H = DGS_TILE_Y / BWD_STRIPS;
+    const unsigned tile_y = blockIdx.y / BWD_STRIPS, strip = blockIdx.y % BWD_STRIPS;
+    const int tile = tile_y * f.tiles_x + blockIdx.x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    BwdWarpSmem& sm = reinterpret_cast<BwdWarpSmem*>(smem_raw)[warp];
+    const unsigned wx0 = blockIdx.x * DGS_TILE_X + (warp & 1) * 8;
+    const unsigned wy0 = tile_y * DGS_TILE_Y + strip * STRIP_H + (warp >> 1) * 4;
+    const unsigned pixx = wx0 + (lane & 7), pixy = wy0 + (lane >> 3);
+    const bool inside = pixx < (unsigned)f.W && pixy < (unsigned)f.H;
+    const size_t HW = (size_t)f.H * f.W;
+    const size_t pix_id = (size_t)f.W * pixy + pixx;
+    const float pixfx = (float)pixx, pixfy = (float)pixy;
+
+    const uint2 range = decode_range(p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile]);
+    const unsigned wbit = strip * BWD_WARPS + warp;      // this warp's index among the 8 warps of the forward's tile block
+
+    const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
+    const int last_contributor = inside ? (int)p.n_contrib[(size_t)s * HW + pix_id] : 0;
+    // nothing behind the warp's deepest contributor can receive gradient from it
+    const int list_len = min((int)(range.y - range.x), __reduce_max_sync(FULL_MASK, last_contributor));
+    if (list_len <= 0) return;      // warp-uniform; the kernel has no block-level barrier
+
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpixd = 0.f;
+    if (inside) {
+        if (p.dL_dpix) {
+            const float* d = p.dL_dpix + (size_t)s * 3 * HW;
+            dpix0 = d[pix_id]; dpix1 = d[HW + pix_id]; dpix2 = d[2 * HW + pix_id];
+        }
+        if (p.dL_dpixdepth) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
+        if (p.dL_dblur) {   // backward of blurred = sum_s color_s / denominator
+            dpix0 += p.dL_dblur[pix_id] / p.blur_denominator;
+            dpix1 += p.dL_dblur[HW + pix_id] / p.blur_denominator;
+            dpix2 += p.dL_dblur[2 * HW + pix_id] / p.blur_denominator;
+        }
+    }
+    sm.dpix[lane] = make_float4(dpix0, dpix1, dpix2, dpixd);
+    float bg_dot_dpixel = 0.f;
+    bg_dot_dpixel += f.background[0] * dpix0;
+    bg_dot_dpixel += f.background[1] * dpix1;
+    bg_dot_dpixel += f.background[2] * dpix2;
+    bg_dot_dpixel += f.z_far * dpixd;
+    float T = T_final;
+    float R = T_final * bg_dot_dpixel;      // suffix sum of the replay (see k_render_bwd)
+    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
+    const float rx0 = (float)wx0, ry0 = (float)wy0;
+
+    const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
+    const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
+    const float4* __restrict__ geo2 = f.geo2 + (size_t)s * f.P;
+    float4* __restrict__ gp0 = p.g0 + (size_t)s * f.P;
+    float4* __restrict__ gp1 = p.g1 + (size_t)s * f.P;
+    float4* __restrict__ gp2 = p.g2 + (size_t)s * f.P;
+    const uint32_t* __restrict__ plist = p.point_list + range.x;
+    const uint8_t* __restrict__ wmask =
+        reinterpret_cast<const uint8_t*>(p.bin_header) + p.bin_header->wmask_offset + range.x;
+
+    uint32_t a_rec, a_idr;
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_rec) : "r"(smem_addr(sm.rec)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_idr) : "r"(smem_addr(sm.idr)));
+
+    // Step k covers the list positions hi_k - lane, hi_k = list_len - 1 - 32 k (back to front); r = 31 - lane is the
+    // position relative to the step's lowest one, low_k = hi_k - 31.  A pixel replays the entries in front of its last
+    // contributor: low_k + r < last_contributor  <=>  r < rel_k, rel_k = last_contributor - low_k (grows by 32 per step).
+    const int steps = (list_len + 31) >> 5;
+    int rel = last_contributor - (list_len - 32);
+    auto load_step = [&](int k, uint32_t& wmb, uint32_t& id) {
+        const int ps = list_len - 1 - 32 * k - (int)lane;
+        wmb = 0u; id = 0u;
+        if (ps >= 0 && k < steps) { wmb = wmask[ps]; id = plist[ps]; }
+    };
+    auto issue_gather = [&](int buf, uint32_t wmb, uint32_t id) -> int {
+        const bool keep = ((wmb >> wbit) & 1u) != 0u;
+        const unsigned mask = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+            const unsigned rank = __popc(mask & ((1u << lane) - 1u));
+            const uint32_t dst = a_rec + (uint32_t)buf * (32u * 48u) + rank * 48u;
+            cp_async16(dst, geo0 + id);
+            cp_async16(dst + 16u, geo1 + id);
+            cp_async16(dst + 32u, geo2 + id);
+            sts_u32(a_idr + (uint32_t)buf * 128u + rank * 4u, id | ((31u - lane) << BWD_ID_BITS));
+        }
+        cp_async_commit();
+        return __popc(mask);
+    };
+
+    uint32_t wmb, idn;
+    load_step(0, wmb, idn);
+    int n_cur = issue_gather(0, wmb, idn);
+    load_step(1, wmb, idn);
+    int qn = 0;   // queued entries (warp-uniform)
+    for (int k = 0; k < steps; k++, rel += 32) {
+        const int n_next = issue_gather((k + 1) & 1, wmb, idn);    // (past the end: no copies, an empty group)
+        load_step(k + 2, wmb, idn);
+        cp_async_wait<1>();
+        __syncwarp();
+        uint32_t rb = a_rec + (uint32_t)(k & 1) * (32u * 48u), ib = a_idr + (uint32_t)(k & 1) * 128u;
+        // The body is branch-free: a hit entry has at least one contributing lane (the forward said so), so skipping
+        // on a warp-wide "nobody contributes" never happens and per-lane decisions are selects.  A lane that does not
+        // contribute carries G = alpha = 0 through the same arithmetic (1 / (1 - 0) = 1: T, R unchanged, w1 = w2 = 0).
+        // Two entries per iteration: their loads, exponents and colour dot products are independent and overlap; only
+        // the T / R recurrences are sequential.
+        auto weigh = [&](uint32_t idr, const float4& g0, const float4& con_o, float& G, float& alpha) {
+            const float dx = g0.x - pixfx, dy = g0.y - pixfy;
+            // exponent and exp() are the forward's, operation for operation (see k_render_bwd)
+            const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+            const float Gx = expf(power);
+            const float ax = min(0.99f, con_o.w * Gx);
+            const bool ok = (int)(idr >> BWD_ID_BITS) < rel && power <= 0.0f && ax >= 1.0f / 255.0f;
+            G = ok ? Gx : 0.f;
+            alpha = ok ? ax : 0.f;
+        };
+        auto replay = [&](float G, float alpha, float opac, float cdot, float& w1, float& w2) {
+            const float inv_1ma = rcp_approx(1.f - alpha);
+            T = T * inv_1ma;
+            w2 = alpha * T;
+            const float dL_dalpha = T * cdot - R * inv_1ma;
+            R = fmaf(w2, cdot, R);
+            w1 = opac * G * dL_dalpha;
+        };
+        auto enqueue = [&](float w1, float w2, uint32_t idr) {
+            sm.qw[qn][lane] = make_float2(w1, w2);
+            sm.qid[qn] = idr & BWD_ID_MASK;              // same value from every lane
+            if (++qn == BWD_QN) {
+                bwd_flush_w(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+                qn = 0;
+            }
+        };
+        int j = 0;
+        for (; j + 2 <= n_cur; j += 2, rb += 96u, ib += 8u) {
+            const uint32_t idrA = lds_u32(ib), idrB = lds_u32(ib + 4u);
+            const float4 g0A = lds_f4_off<0>(rb), conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
+            const float4 g0B = lds_f4_off<48>(rb), conB = lds_f4_off<64>(rb), cB = lds_f4_off<80>(rb);
+            float GA, aA, GB, aB;
+            weigh(idrA, g0A, conA, GA, aA);
+            weigh(idrB, g0B, conB, GB, aB);
+            const float cdotA = cA.x * dpix0 + cA.y * dpix1 + cA.z * dpix2 + g0A.z * dpixd;
+            const float cdotB = cB.x * dpix0 + cB.y * dpix1 + cB.z * dpix2 + g0B.z * dpixd;
+            float w1A, w2A, w1B, w2B;
+            replay(GA, aA, conA.w, cdotA, w1A, w2A);
+            replay(GB, aB, conB.w, cdotB, w1B, w2B);
+            enqueue(w1A, w2A, idrA);
+            enqueue(w1B, w2B, idrB);
+        }
+        if (j < n_cur) {
+            const uint32_t idrA = lds_u32(ib);
+            const float4 g0A = lds_f4_off<0>(rb), conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
+            float GA, aA, w1A, w2A;
+            weigh(idrA, g0A, conA, GA, aA);
+            const float cdotA = cA.x * dpix0 + cA.y * dpix1 + cA.z * dpix2 + g0A.z * dpixd;
+            replay(GA, aA, conA.w, cdotA, w1A, w2A);
+            enqueue(w1A, w2A, idrA);
+        }
+        __syncwarp();      // every lane is done with this buffer before step k+2 is gathered into it
+        n_cur = n_next;
+    }
+    cp_async_wait<0>();
+    if (qn > 0) bwd_flush_w(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+}
+
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
     static_assert(sizeof(BwdSmem) <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device opt-in needed");
+    static_assert(sizeof(BwdWarpSmem) * BWD_WARPS <= 48 * 1024, "fits the default dynamic shared-memory limit");
     dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
-    k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p);
+    static const int variant = [] { const char* e = getenv("DGS_BWD_VARIANT"); return e ? atoi(e) : 1; }();
+    if (variant == 0) { k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p); return; }
+    k_render_bwd_w<<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------
