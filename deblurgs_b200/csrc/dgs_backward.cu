@@ -21,7 +21,6 @@
 // (21 values per sub-frame) are reduced over the warp with a 23-shuffle halving exchange (each
 // step trades half of the remaining components with the partner lane) and accumulated in fp64.
 #include "dgs_internal.cuh"
-#include <cstdlib>
 
 namespace dgs {
 
@@ -76,282 +75,40 @@ struct HalvingReduce {
 };
 
 // ---------------------------------------------------------------------------------------
-// tile blending, backward.  grid = (tiles_x, tiles_y * 8/BWD_WARPS, F), BWD_THREADS threads = one
-// 16 x 8 strip of a tile; each warp owns an 8x4 pixel rectangle and, like the forward, evaluates
-// only the staged entries whose alpha >= 1/255 footprint can reach that rectangle.
+// tile blending, backward.  grid = (tiles_x, tiles_y * 8/BWD_WARPS, F), BWD_THREADS threads = one 16 x 8 strip of a
+// tile; each warp owns an 8x4 pixel rectangle -- the same rectangle as one warp of the forward's tile block -- and
+// works on its own: there is no block-level barrier in this kernel.
 // gradient scratch = three planes of N float4:
 //   g0: dmean2D(x,y), dconic(x,y) | g1: dconic(w), dopacity, ddepth, - | g2: dcolor(r,g,b), -
 // (the geometry half of the per-Gaussian backward reads g0 and g1, the colour half g2: every sector it touches is
-// fully used; as one 48-B record per entry the two halves together pulled 80 B per entry)
+// fully used)
+//
+// Which entries: the forward's hand-over byte says exactly which list entries a warp blended.  Per step a warp reads 32
+// hand-over bytes + list ids (coalesced, back to front), and only the lanes whose entry it blended gather that entry's
+// three 16-B records -- straight into the warp's own shared-memory slots with cp.async (no registers, no barrier),
+// compacted back to front.  The gather of step k+1 and the byte / id loads of step k+2 are in flight while step k is
+// replayed.  (Round 2's first version staged EVERY entry of the tile list for a 4-warp strip behind two
+// __syncthreads per 256 entries: 16 % of the warp cycles waited at those barriers, ~8x more records were gathered
+// than used, and the replay depth was the strip's instead of the warp's: 2.17 -> 1.79 ms at c2.)
 //
 // Gradient accumulation is split in two phases so that no per-entry cross-lane reduction is
 // needed (the reference issues 10 atomics per contributing pixel; a per-entry warp reduction
 // costs ~50 shuffle/select/add instructions per (warp, entry)):
-//   phase 1 (lane = pixel): replay the list back to front (same pairs, same alpha as the forward;
-//           dL/dalpha from un-normalised suffix sums, see the loop) and, for
-//           every entry with a contributing pixel, append ONE column to a per-warp queue in
-//           shared memory: per pixel the two scalars w1 = opacity*G*dL/dalpha and w2 = alpha*T
+//   phase 1 (lane = pixel): replay the gathered entries back to front (same pairs, same alpha as the forward;
+//           dL/dalpha from un-normalised suffix sums, see the loop) and append ONE column per entry to a per-warp
+//           queue in shared memory: per pixel the two scalars w1 = opacity*G*dL/dalpha and w2 = alpha*T
 //           (zeros where the pixel does not contribute), plus the entry's Gaussian index.
-//   phase 2 (lane = queued entry, when 16 entries are queued): each lane walks the pixels of
-//           the rectangle (two half-warps take 16 pixels each), accumulates the moments
-//           sum w1*{1,px,py,px^2,px*py} about the rectangle's corner and sum w2*dL/dpix{r,g,b,depth}
-//           in registers with every lane busy, shifts the moments to the Gaussian's centre
-//           (= sum w1*{1,dx,dy,dx^2,dx*dy,dy^2}), converts them to the 10 gradient components and
-//           issues the REDs.
+//   phase 2 (lane = queued entry x pixel row, when BWD_QN entries are queued): accumulates the moments
+//           sum w1*{1,px,px^2} about the row's first pixel and sum w2*dL/dpix{r,g,b,depth} in registers with every
+//           lane busy, shifts the moments to the Gaussian's centre (= sum w1*{1,dx,dy,dx^2,dx*dy,dy^2}), sums the
+//           four rows, converts to the 10 gradient components and issues three 16-B vector REDs.
 // The sums are the reference's, regrouped.
 // ---------------------------------------------------------------------------------------
 #define BWD_WARPS 4               // warps per block: a block owns a 16 x (4*BWD_WARPS/2) strip of a tile
 #define BWD_THREADS (32 * BWD_WARPS)
 #define BWD_QN 8                  // queued entries per flush
 #define BWD_QSTRIDE 33            // float2 row stride of the queue (bank-conflict-free both ways)
-#define BWD_BATCH 256             // list entries staged per round
 
-struct BwdSmem {
-    uint8_t wm[BWD_BATCH];            // which warps of the tile blended the staged entry (written by the forward)
-    uint32_t id[BWD_BATCH];           // Gaussian index of the staged entry
-    float2 xy[BWD_BATCH];
-    float4 con[BWD_BATCH];
-    float4 rgbd[BWD_BATCH];
-    float2 qw[BWD_WARPS][BWD_QN][BWD_QSTRIDE];   // per warp: [queued entry][pixel] -> (w1, w2)
-    uint32_t qid[BWD_WARPS][BWD_QN];             // per warp: Gaussian index of the queued entry
-    float4 dpix[BWD_WARPS][32];                  // per warp: dL/dpix r,g,b,depth of its 32 pixels
-    int tile_max;
-};
-
-// Phase 2.  Lane (e, quarter) owns queued entry e and the 8 pixels of row `quarter` of the warp's 8x4
-// rectangle (8 queued entries x 4 rows = 32 busy lanes; the queue is half the size of a 16-entry one, which is what
-// bounds the resident warps per SM).  The weighted moments are accumulated about the row's first pixel with the
-// pixel offsets as compile-time constants (sum w, sum w*px, sum w*px^2), and shifted to the
-// Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
-// until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the staging
-// pass fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
-__device__ __forceinline__ void bwd_flush(BwdSmem& sm, unsigned warp, unsigned lane, int qn, float wx0f,
-                                          float wy0f, float ddelx_dx, float ddely_dy,
-                                          const float4* __restrict__ geo0, const float4* __restrict__ geo1,
-                                          float4* __restrict__ gp0, float4* __restrict__ gp1, float4* __restrict__ gp2)
-{
-    __syncwarp();
-    const unsigned e = lane & 7u, quarter = lane >> 3;     // queued entry, pixel row of the warp's 8x4 rectangle
-    const bool live = (int)e < qn;
-    uint32_t id = 0;
-    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-    if (live) {
-        id = sm.qid[warp][e];
-        g0 = __ldg(geo0 + id);   // x, y, depth, radius
-        g1 = __ldg(geo1 + id);   // conic a, b, c, opacity
-    }
-    float M0 = 0.f, Mx = 0.f, Mxx = 0.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Cd = 0.f;
-#pragma unroll
-    for (int pp = 0; pp < 8; pp++) {
-        const float2 w = sm.qw[warp][e][quarter * 8 + pp];
-        const float4 dp = sm.dpix[warp][quarter * 8 + pp];
-        const float px = (float)pp;
-        M0 += w.x;
-        Mx = fmaf(w.x, px, Mx);
-        Mxx = fmaf(w.x, px * px, Mxx);
-        Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
-    }
-    // shift to the centre: pixel px of this row is at distance (bx - px, by) from it
-    const float bx = g0.x - wx0f, by = g0.y - (wy0f + (float)quarter);
-    float S0 = M0;
-    float Sx = bx * M0 - Mx;
-    float Sy = by * M0;
-    float Sxx = bx * (bx * M0 - 2.0f * Mx) + Mxx;
-    float Sxy = by * Sx;
-    float Syy = by * Sy;
-#pragma unroll
-    for (int d = 8; d <= 16; d <<= 1) {      // sum the four rows
-        S0 += __shfl_xor_sync(FULL_MASK, S0, d);   Sx += __shfl_xor_sync(FULL_MASK, Sx, d);
-        Sy += __shfl_xor_sync(FULL_MASK, Sy, d);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, d);
-        Sxy += __shfl_xor_sync(FULL_MASK, Sxy, d); Syy += __shfl_xor_sync(FULL_MASK, Syy, d);
-        Cr += __shfl_xor_sync(FULL_MASK, Cr, d);   Cg += __shfl_xor_sync(FULL_MASK, Cg, d);
-        Cb += __shfl_xor_sync(FULL_MASK, Cb, d);   Cd += __shfl_xor_sync(FULL_MASK, Cd, d);
-    }
-    if (quarter == 0 && live) {
-        const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
-        // three 16-B vector reductions (sm_90+ red.global.add.v4.f32), one per gradient plane, instead of ten scalar ones
-        red_add_v4(reinterpret_cast<float*>(gp0 + id), -(A * Sx + B * Sy) * ddelx_dx, -(Cc * Sy + B * Sx) * ddely_dy,
-                   -0.5f * Sxx, -0.5f * Sxy);
-        red_add_v4(reinterpret_cast<float*>(gp1 + id), -0.5f * Syy, o != 0.f ? S0 / o : 0.f, Cd, 0.f);
-        red_add_v4(reinterpret_cast<float*>(gp2 + id), Cr, Cg, Cb, 0.f);
-    }
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-
-    const FwdParams& f = p.f;
-    const int s = blockIdx.z;
-    // blockIdx.y = tile row * BWD_STRIPS + strip: the 8 / BWD_WARPS strips of a tile are separate blocks that
-    // walk the same tile list.  Fewer warps per barrier (the warps of a block wait for the one with the
-    // most surviving entries every staged batch), and each strip replays only up to ITS deepest contributor.
-    constexpr unsigned BWD_STRIPS = 8 / BWD_WARPS, STRIP_H = DGS_TILE_Y / BWD_STRIPS;
-    const unsigned tile_y = blockIdx.y / BWD_STRIPS, strip = blockIdx.y % BWD_STRIPS;
-    const int tile = tile_y * f.tiles_x + blockIdx.x;
-    const int tid = threadIdx.x;
-    const unsigned lane = tid & 31, warp = tid >> 5;
-    const unsigned wx0 = blockIdx.x * DGS_TILE_X + (warp & 1) * 8;
-    const unsigned wy0 = tile_y * DGS_TILE_Y + strip * STRIP_H + (warp >> 1) * 4;
-    const unsigned pixx = wx0 + (lane & 7), pixy = wy0 + (lane >> 3);
-    const float rx0 = (float)wx0, ry0 = (float)wy0, rx1 = (float)(wx0 + 7), ry1 = (float)(wy0 + 3);
-    const bool inside = pixx < (unsigned)f.W && pixy < (unsigned)f.H;
-    const size_t HW = (size_t)f.H * f.W;
-    const size_t pix_id = (size_t)f.W * pixy + pixx;
-    const float pixfx = (float)pixx, pixfy = (float)pixy;
-
-    const uint2 range = decode_range(p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile]);
-    // shared-window addresses the compiler cannot rematerialise inside the pair loop (it otherwise rebuilds them from
-    // SR_CgaCtaId on every iteration)
-    uint32_t a_xy, a_con, a_rgbd, a_id;
-    asm volatile("mov.u32 %0, %1;" : "=r"(a_xy) : "r"(smem_addr(sm.xy)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(a_con) : "r"(smem_addr(sm.con)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(a_rgbd) : "r"(smem_addr(sm.rgbd)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(a_id) : "r"(smem_addr(sm.id)));
-    const uint8_t* __restrict__ wmask = reinterpret_cast<const uint8_t*>(p.bin_header) + p.bin_header->wmask_offset;
-    const unsigned wbit = strip * BWD_WARPS + warp;      // this warp's index among the 8 warps of the forward's tile block
-
-    const float4* __restrict__ geo0 = f.geo0 + (size_t)s * f.P;
-    const float4* __restrict__ geo1 = f.geo1 + (size_t)s * f.P;
-    const float4* __restrict__ geo2 = f.geo2 + (size_t)s * f.P;
-    float4* __restrict__ gp0 = p.g0 + (size_t)s * f.P;
-    float4* __restrict__ gp1 = p.g1 + (size_t)s * f.P;
-    float4* __restrict__ gp2 = p.g2 + (size_t)s * f.P;
-
-    const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)p.n_contrib[(size_t)s * HW + pix_id] : 0;
-
-    // Nothing behind the deepest contributor of the tile can receive gradient: restrict the
-    // replay to the first `tile_max` list entries (identical results, less staging).
-    if (tid == 0) sm.tile_max = 0;
-    __syncthreads();
-    int warp_max = last_contributor;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) warp_max = max(warp_max, __shfl_xor_sync(FULL_MASK, warp_max, d));
-    if (lane == 0) atomicMax(&sm.tile_max, warp_max);
-    __syncthreads();
-    const int list_len = min((int)(range.y - range.x), sm.tile_max);
-
-    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, dpixd = 0.f;
-    if (inside) {
-        if (p.dL_dpix) {
-            const float* d = p.dL_dpix + (size_t)s * 3 * HW;
-            dpix0 = d[pix_id]; dpix1 = d[HW + pix_id]; dpix2 = d[2 * HW + pix_id];
-        }
-        if (p.dL_dpixdepth) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
-        if (p.dL_dblur) {   // backward of blurred = sum_s color_s / denominator
-            dpix0 += p.dL_dblur[pix_id] / p.blur_denominator;
-            dpix1 += p.dL_dblur[HW + pix_id] / p.blur_denominator;
-            dpix2 += p.dL_dblur[2 * HW + pix_id] / p.blur_denominator;
-        }
-    }
-    sm.dpix[warp][lane] = make_float4(dpix0, dpix1, dpix2, dpixd);
-    float bg_dot_dpixel = 0.f;
-    bg_dot_dpixel += f.background[0] * dpix0;
-    bg_dot_dpixel += f.background[1] * dpix1;
-    bg_dot_dpixel += f.background[2] * dpix2;
-    bg_dot_dpixel += f.z_far * dpixd;
-
-    // Suffix sum of the replay (see the loop below): everything behind the current entry, dotted with
-    // dL/dpix.  Behind the last contributor there is only the background.
-    float R = T_final * bg_dot_dpixel;
-    const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
-
-    const int rounds = (list_len + BWD_BATCH - 1) / BWD_BATCH;
-    int todo = list_len;
-    int qn = 0;   // queued entries of this warp (warp-uniform)
-
-    for (int i = 0; i < rounds; i++, todo -= BWD_BATCH) {
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BWD_BATCH / BWD_THREADS; k++) {
-            const int slot = k * BWD_THREADS + tid;
-            const int progress = i * BWD_BATCH + slot;
-            if (progress < list_len) {
-                const uint32_t lp = range.x + list_len - progress - 1;
-                const uint32_t id = p.point_list[lp];
-                sm.wm[slot] = wmask[lp];
-                const float4 a = geo0[id];
-                const float4 c = geo2[id];
-                sm.id[slot] = id;
-                sm.xy[slot] = make_float2(a.x, a.y);
-                sm.con[slot] = geo1[id];
-                sm.rgbd[slot] = make_float4(c.x, c.y, c.z, a.z);
-            }
-        }
-        __syncthreads();
-        const int batch = min(BWD_BATCH, todo);
-        // entry j of this batch sits at list position first_pos - j (the batch is staged back to front)
-        const int first_pos = list_len - i * BWD_BATCH - 1;
-        for (int c0 = 0; c0 < batch; c0 += 32) {
-            const int jl = c0 + (int)lane;
-            // the forward recorded which (warp, entry) pairs blended at least one pixel: visit exactly those
-            const bool keep = jl < batch && ((sm.wm[jl] >> wbit) & 1u);
-            unsigned mask = __ballot_sync(FULL_MASK, keep);
-            while (mask) {
-                const int j = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int contributor = first_pos - j;
-                const float2 xy = lds_f2(a_xy + 8u * (uint32_t)j);
-                const float4 con_o = lds_f4(a_con + 16u * (uint32_t)j);
-                const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                float G = 0.f, alpha = 0.f;
-                if (inside && contributor < last_contributor) {
-                    // Exponent and exp() are the forward's (= the reference's), operation for operation: the replay
-                    // must classify every pair exactly as the forward did.  One pair whose alpha falls on the other
-                    // side of 1/255 injects a bogus w * (c . dL/dpix) into R and moves dL/dalpha of EVERY entry in
-                    // front of it at that pixel by up to ~10 % (measured with ex2.approx here: ~100 such pixels per
-                    // c2 view, individual Gaussian gradients off by 2 %, for 0.14 ms) -- not worth it.
-                    const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
-                    if (power <= 0.0f) {
-                        G = expf(power);
-                        alpha = min(0.99f, con_o.w * G);
-                    }
-                }
-                const bool contrib = alpha >= 1.0f / 255.0f;     // (some lane contributes: the forward said so)
-                float w1 = 0.f, w2 = 0.f;
-                if (contrib) {
-                    // The reference replays T and the colour accumulated BEHIND the entry as normalised
-                    // recurrences (accum_rec, backward.cu:585-600) and divides twice by (1 - alpha).  The
-                    // same derivative written on un-normalised sums needs one dot product and one
-                    // reciprocal:  with T_i the transmittance in front of entry i, w_j = alpha_j T_j and
-                    // R_i = sum_{j behind i} w_j (c_j . dL/dpix) + T_final (bg . dL/dpix),
-                    //   dL/dalpha_i = T_i (c_i . dL/dpix) - R_i / (1 - alpha_i),   R_{i-1} = R_i + w_i (c_i . dL/dpix).
-                    // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp) is far inside the 1e-3
-                    // gradient tolerance.
-                    const float inv_1ma = rcp_approx(1.f - alpha);
-                    T = T * inv_1ma;
-                    w2 = alpha * T;
-                    const float4 cd = lds_f4(a_rgbd + 16u * (uint32_t)j);
-                    const float cdot = cd.x * dpix0 + cd.y * dpix1 + cd.z * dpix2 + cd.w * dpixd;
-                    const float dL_dalpha = T * cdot - R * inv_1ma;
-                    R = fmaf(w2, cdot, R);
-                    w1 = con_o.w * G * dL_dalpha;
-                }
-                sm.qw[warp][qn][lane] = make_float2(w1, w2);
-                sm.qid[warp][qn] = lds_u32(a_id + 4u * (uint32_t)j);   // same value from every lane
-                if (++qn == BWD_QN) {
-                    bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
-                    qn = 0;
-                }
-            }
-        }
-    }
-    if (qn > 0) bwd_flush(sm, warp, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
-}
-
-// ---------------------------------------------------------------------------------------
-// Warp-independent variant (round 2, second half).  The forward's hand-over byte says exactly which list entries a
-// warp blended, so a warp no longer needs the block's staged copy of the WHOLE tile list: it reads 32 hand-over bytes
-// + list ids per step (coalesced), and only the lanes whose entry it blended gather that entry's three 16-B records --
-// straight into the warp's own shared-memory slots with cp.async (no registers, no block barrier), compacted back to
-// front.  The gather of step k+1 and the byte / id loads of step k+2 are in flight while step k is replayed.  Nothing
-// is shared between warps any more: no __syncthreads, no strip-wide replay depth (each warp starts at ITS deepest
-// contributor), and ~8x fewer gathered records than staging every entry for every strip.
-// ---------------------------------------------------------------------------------------
 struct __align__(16) BwdWarpSmem {
     float4 rec[2][32][3];                 // [buffer][compacted entry] -> geo0 | geo1 | geo2 records (cp.async targets)
     uint32_t idr[2][32];                  // Gaussian index | (list position relative to the step's lowest) << 27
@@ -374,8 +131,13 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// Phase 2 of the warp-independent kernel: same arithmetic as bwd_flush above, on the warp's own queue.
-__device__ __forceinline__ void bwd_flush_w(BwdWarpSmem& sm, unsigned lane, int qn, float wx0f, float wy0f,
+// Phase 2.  Lane (e, quarter) owns queued entry e and the 8 pixels of row `quarter` of the warp's 8x4
+// rectangle (8 queued entries x 4 rows = 32 busy lanes).  The weighted moments are accumulated about the row's first
+// pixel with the pixel offsets as compile-time constants (sum w, sum w*px, sum w*px^2), and shifted to the
+// Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
+// until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the gather
+// fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
+__device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn, float wx0f, float wy0f,
                                             float ddelx_dx, float ddely_dy, const float4* __restrict__ geo0,
                                             const float4* __restrict__ geo1, float4* __restrict__ gp0,
                                             float4* __restrict__ gp1, float4* __restrict__ gp2)
@@ -426,7 +188,7 @@ __device__ __forceinline__ void bwd_flush_w(BwdWarpSmem& sm, unsigned lane, int 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
+__global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FwdParams& f = p.f;
@@ -473,7 +235,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
     bg_dot_dpixel += f.background[2] * dpix2;
     bg_dot_dpixel += f.z_far * dpixd;
     float T = T_final;
-    float R = T_final * bg_dot_dpixel;      // suffix sum of the replay (see k_render_bwd)
+    float R = T_final * bg_dot_dpixel;      // suffix sum of the replay (see `replay` below): behind the last contributor there is only the background
     const float ddelx_dx = 0.5f * f.W, ddely_dy = 0.5f * f.H;
     const float rx0 = (float)wx0, ry0 = (float)wy0;
 
@@ -534,7 +296,10 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
         // the T / R recurrences are sequential.
         auto weigh = [&](uint32_t idr, const float4& g0, const float4& con_o, float& G, float& alpha) {
             const float dx = g0.x - pixfx, dy = g0.y - pixfy;
-            // exponent and exp() are the forward's, operation for operation (see k_render_bwd)
+            // Exponent and exp() are the forward's (= the reference's), operation for operation: the replay must
+            // classify every pair exactly as the forward did.  One pair whose alpha falls on the other side of 1/255
+            // injects a bogus w * (c . dL/dpix) into R and moves dL/dalpha of EVERY entry in front of it at that pixel
+            // by up to ~10 % (measured with ex2.approx: ~100 such pixels per c2 view, for 0.14 ms) -- not worth it.
             const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
             const float Gx = expf(power);
             const float ax = min(0.99f, con_o.w * Gx);
@@ -542,6 +307,12 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
             G = ok ? Gx : 0.f;
             alpha = ok ? ax : 0.f;
         };
+        // The reference replays T and the colour accumulated BEHIND the entry as normalised recurrences (accum_rec,
+        // backward.cu:585-600) and divides twice by (1 - alpha).  The same derivative written on un-normalised sums
+        // needs one dot product and one reciprocal: with T_i the transmittance in front of entry i, w_j = alpha_j T_j
+        // and R_i = sum_{j behind i} w_j (c_j . dL/dpix) + T_final (bg . dL/dpix),
+        //   dL/dalpha_i = T_i (c_i . dL/dpix) - R_i / (1 - alpha_i),   R_{i-1} = R_i + w_i (c_i . dL/dpix).
+        // 1 - alpha is in [0.01, 1]: the approximate reciprocal (1 ulp) is far inside the 1e-3 gradient tolerance.
         auto replay = [&](float G, float alpha, float opac, float cdot, float& w1, float& w2) {
             const float inv_1ma = rcp_approx(1.f - alpha);
             T = T * inv_1ma;
@@ -554,7 +325,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
             sm.qw[qn][lane] = make_float2(w1, w2);
             sm.qid[qn] = idr & BWD_ID_MASK;              // same value from every lane
             if (++qn == BWD_QN) {
-                bwd_flush_w(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+                bwd_flush(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
                 qn = 0;
             }
         };
@@ -587,19 +358,16 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd_w(const BwdParams p)
         n_cur = n_next;
     }
     cp_async_wait<0>();
-    if (qn > 0) bwd_flush_w(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+    if (qn > 0) bwd_flush(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
 {
     const FwdParams& f = p.f;
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
-    static_assert(sizeof(BwdSmem) <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device opt-in needed");
-    static_assert(sizeof(BwdWarpSmem) * BWD_WARPS <= 48 * 1024, "fits the default dynamic shared-memory limit");
+    static_assert(sizeof(BwdWarpSmem) * BWD_WARPS <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device opt-in needed");
     dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
-    static const int variant = [] { const char* e = getenv("DGS_BWD_VARIANT"); return e ? atoi(e) : 1; }();
-    if (variant == 0) { k_render_bwd<<<grid, block, sizeof(BwdSmem), st>>>(p); return; }
-    k_render_bwd_w<<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
+    k_render_bwd<<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------
