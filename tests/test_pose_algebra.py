@@ -72,6 +72,31 @@ def test_quaternion_convention_is_xyzw_and_round_trips():
         assert (pose.rotmat_to_unitquat(pose.unitquat_to_rotmat(v)) - v).abs().max().item() < 1e-12
 
 
+def test_quaternion_conversions_match_scipy_rotation():
+    """`roma` (the reference's quaternion library, scene/motion.py:192,245, test.py:66,79) is not installed here and the
+    reference does not pin its version; its documented conventions are XYZW order and a matrix -> quaternion routine
+    "adapted from SciPy".  scipy.spatial.transform.Rotation is installed and uses the same conventions: pin both
+    conversions against it (q and -q are the same rotation)."""
+    Rot = pytest.importorskip("scipy.spatial.transform").Rotation
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(512, 4, generator=g, dtype=torch.float64)
+    q = q / q.norm(dim=-1, keepdim=True)
+    R_sp = torch.from_numpy(Rot.from_quat(q.numpy()).as_matrix())
+    assert (pose.unitquat_to_rotmat(q) - R_sp).abs().max().item() < 1e-14
+    mine = pose.rotmat_to_unitquat(R_sp)
+    theirs = torch.from_numpy(Rot.from_matrix(R_sp.numpy()).as_quat())
+    theirs = torch.where(theirs[:, 3:4] < 0, -theirs, theirs)
+    assert (mine - theirs).abs().max().item() < 1e-12
+    # near-pi rotations exercise the three non-trace branches
+    axes = torch.nn.functional.normalize(torch.randn(64, 3, generator=g, dtype=torch.float64), dim=-1)
+    ang = math.pi - torch.rand(64, 1, generator=g, dtype=torch.float64) * 1e-3
+    R_pi = torch.from_numpy(Rot.from_rotvec((axes * ang).numpy()).as_matrix())
+    mine = pose.rotmat_to_unitquat(R_pi)
+    theirs = torch.from_numpy(Rot.from_matrix(R_pi.numpy()).as_quat())
+    sign = torch.sign((mine * theirs).sum(-1, keepdim=True))
+    assert (mine - sign * theirs).abs().max().item() < 1e-9
+
+
 class _RefCam:
     def __init__(self, cam):
         self.image_width, self.image_height = cam.width, cam.height
