@@ -10,85 +10,45 @@
 //                       full_proj = wvt @ projection_matrix in fp32)
 //   camera centre       scene/cameras.py:63-74  (inverse(wvt)[3,:3] == t analytically)
 // The reference evaluates this with ~30 tiny torch kernels and a Python loop per sub-frame and
-// differentiates it with autograd; here one thread per sub-frame evaluates it in fp64 with
-// forward-mode dual numbers (6 tangents), which yields the Jacobian the backward pass needs
-// without any tape.
+// differentiates it with autograd; here eight threads per sub-frame evaluate it in fp64 with
+// forward-mode dual numbers (one tangent direction per thread: the six se(3) components and the curve
+// parameter), which yields the Jacobian the backward pass needs without any tape.  The kernels are pure
+// latency (a few hundred dependent fp64 operations): spreading the tangents and the Bernstein weights over
+// threads is what shortens them (0.030 + 0.047 ms -> see DESIGN.md at F = 16).
 #include "dgs_b200.h"
 #include "dgs_internal.cuh"
 #include <string>
 
 namespace dgs {
 
+// One tangent per thread: the 7 tangent directions of a sub-frame (6 se(3) components + the curve parameter nu, whose
+// seed is d se3 / d nu) are carried by 7 threads that each repeat the (cheap) value arithmetic -- the same fp64 operations in
+// the same order on every thread, so the values do not depend on the split.
 struct Dual {
     double v;
-    double d[6];
+    double d;
 };
-__device__ __forceinline__ Dual dconst(double c)
-{
-    Dual r; r.v = c;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = 0.0;
-    return r;
-}
-__device__ __forceinline__ Dual dvar(double c, int idx)
-{
-    Dual r = dconst(c); r.d[idx] = 1.0; return r;
-}
-__device__ __forceinline__ Dual operator+(const Dual& a, const Dual& b)
-{
-    Dual r; r.v = a.v + b.v;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] + b.d[i];
-    return r;
-}
-__device__ __forceinline__ Dual operator-(const Dual& a, const Dual& b)
-{
-    Dual r; r.v = a.v - b.v;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] - b.d[i];
-    return r;
-}
-__device__ __forceinline__ Dual operator-(const Dual& a)
-{
-    Dual r; r.v = -a.v;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = -a.d[i];
-    return r;
-}
-__device__ __forceinline__ Dual operator*(const Dual& a, const Dual& b)
-{
-    Dual r; r.v = a.v * b.v;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
-    return r;
-}
+__device__ __forceinline__ Dual dconst(double c) { return Dual{c, 0.0}; }
+__device__ __forceinline__ Dual operator+(const Dual& a, const Dual& b) { return Dual{a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ Dual operator-(const Dual& a, const Dual& b) { return Dual{a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ Dual operator-(const Dual& a) { return Dual{-a.v, -a.d}; }
+__device__ __forceinline__ Dual operator*(const Dual& a, const Dual& b) { return Dual{a.v * b.v, a.d * b.v + a.v * b.d}; }
 __device__ __forceinline__ Dual operator/(const Dual& a, const Dual& b)
 {
-    Dual r; const double inv = 1.0 / b.v; r.v = a.v * inv;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
-    return r;
+    const double inv = 1.0 / b.v, q = a.v * inv;
+    return Dual{q, (a.d - q * b.d) * inv};
 }
 __device__ __forceinline__ Dual dsqrt(const Dual& a)
 {
-    Dual r; r.v = sqrt(a.v); const double k = 0.5 / r.v;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] * k;
-    return r;
+    const double r = sqrt(a.v);
+    return Dual{r, a.d * (0.5 / r)};
 }
-__device__ __forceinline__ Dual dsin(const Dual& a)
+__device__ __forceinline__ void dsincos(const Dual& a, Dual& s, Dual& c)
 {
-    Dual r; r.v = sin(a.v); const double k = cos(a.v);
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] * k;
-    return r;
-}
-__device__ __forceinline__ Dual dcos(const Dual& a)
-{
-    Dual r; r.v = cos(a.v); const double k = -sin(a.v);
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.d[i] = a.d[i] * k;
-    return r;
+    double sv, cv;
+    sincos(a.v, &sv, &cv);
+    s = Dual{sv, a.d * cv};
+    c = Dual{cv, a.d * -sv};
 }
 
 __device__ __forceinline__ double binom(int n, int k)
@@ -97,51 +57,89 @@ __device__ __forceinline__ double binom(int n, int k)
     for (int i = 1; i <= k; i++) r = r * (double)(n - k + i) / (double)i;
     return rint(r);
 }
-
-// Bernstein weight of control point k at t, and its derivative w.r.t. t.
-__device__ __forceinline__ void bezier_coeff(float t, int C, int k, double& coeff, double& dcoeff)
+__device__ __forceinline__ double ipow(double x, int n)      // x^n, n >= 0 (square and multiply)
 {
-    const float a = powf(t, (float)(C - k));
-    const float b = powf(1.0f - t, (float)k);
-    const double bn = binom(C, k);
-    coeff = (double)(a * b) * bn;
+    double r = 1.0;
+    while (n > 0) {
+        if (n & 1) r *= x;
+        x *= x;
+        n >>= 1;
+    }
+    return r;
+}
+
+// Bernstein weight of control point k at t (powers and their product in fp32 like the reference, times an fp64 binomial)
+__device__ __forceinline__ double bezier_coeff(float t, int C, int k, float& a, float& b, double& bn)
+{
+    a = powf(t, (float)(C - k));
+    b = powf(1.0f - t, (float)k);
+    bn = binom(C, k);
+    return (double)(a * b) * bn;
+}
+// ... and its derivative w.r.t. t
+__device__ __forceinline__ double bezier_dcoeff(float t, int C, int k, float a, float b, double bn)
+{
     const double td = (double)t, omt = (double)(1.0f - t);
-    double da = (C - k) > 0 ? (double)(C - k) * pow(td, (double)(C - k - 1)) : 0.0;
-    double db = k > 0 ? -(double)k * pow(omt, (double)(k - 1)) : 0.0;
-    dcoeff = bn * (da * (double)b + (double)a * db);
+    const double da = (C - k) > 0 ? (double)(C - k) * ipow(td, C - k - 1) : 0.0;
+    const double db = k > 0 ? -(double)k * ipow(omt, k - 1) : 0.0;
+    return bn * (da * (double)b + (double)a * db);
 }
 
 #define POSE_ROWS 35
 #define POSE_COLS 7
+#define POSE_LANES 8          // threads per sub-frame (7 tangents + 1 idle): a power of two for the width-limited shuffles
+#define POSE_FWD_THREADS 64
 
-__global__ void k_pose_forward(int F, int C, const float* __restrict__ ctrl_trans,
+// thread (s, d): sub-frame s, tangent d.
+__global__ void __launch_bounds__(POSE_FWD_THREADS) k_pose_forward(int F, int C, const float* __restrict__ ctrl_trans,
                                const float* __restrict__ ctrl_rot, const float* __restrict__ nu,
                                const float* __restrict__ proj_t, float* __restrict__ view,
                                float* __restrict__ proj, float* __restrict__ campos,
                                double* __restrict__ jac)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= F) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s_raw = gt / POSE_LANES, d = gt % POSE_LANES;
+    const bool live = s_raw < F;
+    const int s = live ? s_raw : F - 1;         // (every lane takes part in the shuffles)
     const float t = nu[s];
+    // Bezier sample: the lanes of a sub-frame evaluate the Bernstein weights of different control points (the powf /
+    // binomial work), then every lane accumulates all of them in control-point order -- the reference's fp64 sum.
     double se3[6] = {0, 0, 0, 0, 0, 0}, dse3_dnu[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = 0; k <= C; k++) {
-        double c, dc;
-        bezier_coeff(t, C, k, c, dc);
-        for (int d = 0; d < 3; d++) {
-            const double ct = (double)ctrl_trans[3 * k + d], cr = (double)ctrl_rot[3 * k + d];
-            se3[d] += c * ct;       dse3_dnu[d] += dc * ct;
-            se3[3 + d] += c * cr;   dse3_dnu[3 + d] += dc * cr;
+    for (int k0 = 0; k0 <= C; k0 += POSE_LANES) {
+        double c = 0.0, dc = 0.0;
+        if (k0 + d <= C) {
+            float a, b; double bn;
+            c = bezier_coeff(t, C, k0 + d, a, b, bn);
+            dc = bezier_dcoeff(t, C, k0 + d, a, b, bn);
+        }
+        for (int j = 0; j < POSE_LANES; j++) {
+            const double cj = __shfl_sync(0xffffffffu, c, j, POSE_LANES);
+            const double dcj = __shfl_sync(0xffffffffu, dc, j, POSE_LANES);
+            const int k = k0 + j;
+            if (k <= C) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double ct = (double)ctrl_trans[3 * k + i], cr = (double)ctrl_rot[3 * k + i];
+                    se3[i] += cj * ct;       dse3_dnu[i] += dcj * ct;
+                    se3[3 + i] += cj * cr;   dse3_dnu[3 + i] += dcj * cr;
+                }
+            }
         }
     }
     Dual u[3], w[3];
-    for (int d = 0; d < 3; d++) { u[d] = dvar(se3[d], d); w[d] = dvar(se3[3 + d], 3 + d); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        u[i] = Dual{se3[i], d == 6 ? dse3_dnu[i] : (d == i ? 1.0 : 0.0)};
+        w[i] = Dual{se3[3 + i], d == 6 ? dse3_dnu[3 + i] : (d == 3 + i ? 1.0 : 0.0)};
+    }
 
     Dual nrms = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     if (nrms.v < 1e-4) nrms = dconst(1e-4);   // clamp: constant value, zero gradient
     const Dual theta = dsqrt(nrms);
     const Dual one = dconst(1.0);
     const Dual inv = one / theta;
-    const Dual st = dsin(theta), ct = dcos(theta);
+    Dual st, ct;
+    dsincos(theta, st, ct);
     const Dual fac1 = inv * st;
     const Dual fac2 = inv * inv * (one - ct);
     const Dual facV1 = (one - ct) / (theta * theta);
@@ -153,94 +151,120 @@ __global__ void k_pose_forward(int F, int C, const float* __restrict__ ctrl_tran
     K[0][0] = zero;  K[0][1] = -w[2]; K[0][2] = w[1];
     K[1][0] = w[2];  K[1][1] = zero;  K[1][2] = -w[0];
     K[2][0] = -w[1]; K[2][1] = w[0];  K[2][2] = zero;
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) K2[i][j] = K[i][0] * K[0][j] + K[i][1] * K[1][j] + K[i][2] * K[2][j];
     Dual R[3][3], V[3][3];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) {
             const Dual eye = dconst(i == j ? 1.0 : 0.0);
             R[i][j] = fac1 * K[i][j] + fac2 * K2[i][j] + eye;
             V[i][j] = eye + K[i][j] * facV1 + K2[i][j] * facV2;
         }
     Dual T[3];
+#pragma unroll
     for (int i = 0; i < 3; i++) T[i] = V[i][0] * u[0] + V[i][1] * u[1] + V[i][2] * u[2];
 
     // wvt (row-major, row-vector convention): [:3,:3] = R, [3,:3] = -T @ R, last column (0,0,0,1)
     Dual wvt[4][4];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) wvt[i][j] = R[i][j];
+#pragma unroll
     for (int j = 0; j < 3; j++) wvt[3][j] = (-T[0]) * R[0][j] + (-T[1]) * R[1][j] + (-T[2]) * R[2][j];
+#pragma unroll
     for (int i = 0; i < 3; i++) wvt[i][3] = zero;
     wvt[3][3] = one;
+    if (!live) return;
 
-    float wf[4][4];
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            wf[i][j] = (float)wvt[i][j].v;
-            view[16 * s + 4 * i + j] = wf[i][j];
-        }
-    // full_proj = wvt @ proj_t in fp32 (ascending-k fused multiply-add chain)
-    for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) {
-            float acc = 0.f;
-            for (int k = 0; k < 4; k++) acc = fmaf(wf[i][k], proj_t[4 * k + j], acc);
-            proj[16 * s + 4 * i + j] = acc;
-        }
-    for (int d = 0; d < 3; d++) campos[3 * s + d] = (float)T[d].v;
-
-    if (jac != nullptr) {
-        double* J = jac + (size_t)s * POSE_ROWS * POSE_COLS;
+    if (d == 0) {
+        float wf[4][4];
+#pragma unroll
         for (int i = 0; i < 4; i++)
+#pragma unroll
             for (int j = 0; j < 4; j++) {
-                double* row = J + (4 * i + j) * POSE_COLS;
-                double dn = 0.0;
-                for (int d = 0; d < 6; d++) { row[d] = wvt[i][j].d[d]; dn += wvt[i][j].d[d] * dse3_dnu[d]; }
-                row[6] = dn;
-                // d full_proj[i][j] = sum_k d wvt[i][k] * proj_t[k][j]
-                double* prow = J + (16 + 4 * i + j) * POSE_COLS;
-                double pn = 0.0;
-                for (int d = 0; d < 6; d++) {
-                    double a = 0.0;
-                    for (int k = 0; k < 4; k++) a += wvt[i][k].d[d] * (double)proj_t[4 * k + j];
-                    prow[d] = a;
-                    pn += a * dse3_dnu[d];
-                }
-                prow[6] = pn;
+                wf[i][j] = (float)wvt[i][j].v;
+                view[16 * s + 4 * i + j] = wf[i][j];
             }
-        for (int e = 32; e < POSE_ROWS; e++)
-            for (int d = 0; d < POSE_COLS; d++) J[e * POSE_COLS + d] = 0.0;   // campos: no gradient in the reference
+        // full_proj = wvt @ proj_t in fp32 (ascending-k fused multiply-add chain)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc = fmaf(wf[i][k], proj_t[4 * k + j], acc);
+                proj[16 * s + 4 * i + j] = acc;
+            }
+#pragma unroll
+        for (int i = 0; i < 3; i++) campos[3 * s + i] = (float)T[i].v;
+    }
+
+    if (jac != nullptr && d < POSE_COLS) {      // column d of the sub-frame's Jacobian
+        double* J = jac + (size_t)s * POSE_ROWS * POSE_COLS + d;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                J[(4 * i + j) * POSE_COLS] = wvt[i][j].d;
+                // d full_proj[i][j] = sum_k d wvt[i][k] * proj_t[k][j]
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) a += wvt[i][k].d * (double)proj_t[4 * k + j];
+                J[(16 + 4 * i + j) * POSE_COLS] = a;
+            }
+        for (int e = 32; e < POSE_ROWS; e++) J[e * POSE_COLS] = 0.0;   // campos: no gradient in the reference
     }
 }
 
 // One block. dL/dse3[s] = J_s^T [dL/dview_s ; dL/dproj_s]; dL/dctrl[k] = sum_s coeff[s,k] dL/dse3[s].
-__global__ void k_pose_backward(int F, int C, const float* __restrict__ nu, const double* __restrict__ jac,
+// Shared memory: acc [F][7] doubles, then (when it fits: `table` != 0) the Bernstein weights [F][C+1].
+#define POSE_BWD_THREADS 256
+__global__ void __launch_bounds__(POSE_BWD_THREADS) k_pose_backward(int F, int C, int table, const float* __restrict__ nu,
+                                const double* __restrict__ jac,
                                 const float* __restrict__ dview, const float* __restrict__ dproj,
                                 float* __restrict__ dctrl_trans, float* __restrict__ dctrl_rot,
                                 float* __restrict__ dnu)
 {
-    extern __shared__ double sm[];   // [F][7]
-    for (int s = threadIdx.x; s < F; s += blockDim.x) {
-        const double* J = jac + (size_t)s * POSE_ROWS * POSE_COLS;
-        double acc[POSE_COLS];
-        for (int d = 0; d < POSE_COLS; d++) acc[d] = 0.0;
+    extern __shared__ double sm[];   // [F][7] (+ [F][C+1])
+    double* coef = sm + (size_t)F * POSE_COLS;
+    for (int i = threadIdx.x; i < F * POSE_COLS; i += blockDim.x) {
+        const int s = i / POSE_COLS, d = i % POSE_COLS;
+        const double* J = jac + (size_t)s * POSE_ROWS * POSE_COLS + d;
+        double acc = 0.0;
         for (int e = 0; e < 32; e++) {
             const double gsrc = e < 16 ? (double)dview[16 * s + e] : (double)dproj[16 * s + e - 16];
-            for (int d = 0; d < POSE_COLS; d++) acc[d] += J[e * POSE_COLS + d] * gsrc;
+            acc += J[e * POSE_COLS] * gsrc;
         }
-        for (int d = 0; d < POSE_COLS; d++) sm[s * POSE_COLS + d] = acc[d];
-        if (dnu) dnu[s] = (float)acc[6];
+        sm[i] = acc;
+        if (d == 6 && dnu) dnu[s] = (float)acc;
+    }
+    if (table) {
+        for (int i = threadIdx.x; i < F * (C + 1); i += blockDim.x) {
+            float a, b; double bn;
+            coef[i] = bezier_coeff(nu[i / (C + 1)], C, i % (C + 1), a, b, bn);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (C + 1) * 6; i += blockDim.x) {
         const int k = i / 6, d = i % 6;
-        double a = 0.0;
+        double acc = 0.0;
         for (int s = 0; s < F; s++) {
-            double c, dc;
-            bezier_coeff(nu[s], C, k, c, dc);
-            a += c * sm[s * POSE_COLS + d];
+            double c;
+            if (table) {
+                c = coef[s * (C + 1) + k];
+            } else {
+                float a, b; double bn;
+                c = bezier_coeff(nu[s], C, k, a, b, bn);
+            }
+            acc += c * sm[s * POSE_COLS + d];
         }
-        if (d < 3) dctrl_trans[3 * k + d] = (float)a;
-        else dctrl_rot[3 * k + d - 3] = (float)a;
+        if (d < 3) dctrl_trans[3 * k + d] = (float)acc;
+        else dctrl_rot[3 * k + d - 3] = (float)acc;
     }
 }
 
@@ -258,9 +282,9 @@ int dgs_pose_forward(int F, int curve_order, const float* ctrl_trans, const floa
         return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_forward: invalid argument");
     {
         dgs::StageTimer timer(dgs::ST_POSE_FWD, (cudaStream_t)stream, 1);
-        dgs::k_pose_forward<<<(F + 63) / 64, 64, 0, (cudaStream_t)stream>>>(F, curve_order, ctrl_trans, ctrl_rot, nu,
-                                                                            proj_t, viewmatrix, projmatrix, campos,
-                                                                            jacobian);
+        const int threads = F * POSE_LANES;
+        dgs::k_pose_forward<<<(threads + POSE_FWD_THREADS - 1) / POSE_FWD_THREADS, POSE_FWD_THREADS, 0, (cudaStream_t)stream>>>(
+            F, curve_order, ctrl_trans, ctrl_rot, nu, proj_t, viewmatrix, projmatrix, campos, jacobian);
     }
     { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_pose_forward"); }
 }
@@ -276,8 +300,11 @@ int dgs_pose_backward(int F, int curve_order, const float* ctrl_trans, const flo
     if (F > 0 && (!nu || !jacobian || !dL_dviewmatrix || !dL_dprojmatrix)) return dgs::fail(DGS_ERR_INVALID_ARGUMENT, "dgs_pose_backward: invalid argument");
     {
         dgs::StageTimer timer(dgs::ST_POSE_BWD, (cudaStream_t)stream, 1);
-        dgs::k_pose_backward<<<1, 128, (size_t)(F > 0 ? F : 1) * POSE_COLS * sizeof(double), (cudaStream_t)stream>>>(
-            F, curve_order, nu, jacobian, dL_dviewmatrix, dL_dprojmatrix, dL_dctrl_trans, dL_dctrl_rot, dL_dnu);
+        const size_t acc_bytes = (size_t)(F > 0 ? F : 1) * POSE_COLS * sizeof(double);
+        const size_t tab_bytes = (size_t)F * (curve_order + 1) * sizeof(double);
+        const int table = acc_bytes + tab_bytes <= 40 * 1024;       // else the weights are re-evaluated in the sum
+        dgs::k_pose_backward<<<1, POSE_BWD_THREADS, acc_bytes + (table ? tab_bytes : 0), (cudaStream_t)stream>>>(
+            F, curve_order, table, nu, jacobian, dL_dviewmatrix, dL_dprojmatrix, dL_dctrl_trans, dL_dctrl_rot, dL_dnu);
     }
     { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_pose_backward"); }
 }
