@@ -147,36 +147,34 @@ def flat_grad_views(params):
 
 
 def make_step_ours(w, world, lambda_t_smooth=0.0, use_graph=False):
-    """views-dp step.  world > 1: the Gaussian gradients live in one flat buffer (deblurgs_b200.dist.FlatGradBuffer).
-      * graph mode (default): the step is one CUDA-graph replay and the buffer is all-reduced right after it;
-      * kernel-by-kernel mode: the buffer doubles as the backward's gradient SINK -- rows are all-reduced over NCCL
-        while the rest of the per-Gaussian backward still runs (the c3 / c4 lines use this; capturing those
-        collectives inside the graph hung on this NCCL build, and at c2 the replay's lower launch cost is worth as
-        much as the overlap: 5.52 vs 5.54 ms per step on 8 GPUs)."""
+    """views-dp step.  world > 1: the Gaussian gradients live in one flat buffer (deblurgs_b200.dist.FlatGradBuffer) that
+    is the backward's gradient SINK: finished rows are all-reduced over NCCL (called directly, on a side stream) while
+    the rest of the per-Gaussian backward still runs.  In graph mode (default) those collectives are nodes of the same
+    CUDA graph as the step's kernels: one replay per step on every rank."""
     from deblurgs_b200 import dist as dd
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     gparams = g.parameters()
     cparams = cmm.parameters()
     sink = dd.FlatGradBuffer.for_gaussians(g) if world > 1 else None
-    g.grad_sink = sink if not use_graph else None
+    if sink is not None and os.environ.get("DGS_SINK_RANGES"):
+        sink.n_ranges = int(os.environ["DGS_SINK_RANGES"])
+    g.grad_sink = sink
+    overlap = "; NCCL all-reduce of finished gradient rows on a side stream under the per-Gaussian backward" if sink is not None else ""
 
     if use_graph:
         from deblurgs_b200.graph import BlurryViewGraph
         graph = BlurryViewGraph(cmm, 0, w["bg"], (3, w["H"], w["W"]), lambda_t_smooth,
-                                pre_backward=(sink.zero if sink is not None else None),
+                                post_backward=(sink.wait if sink is not None else None),
                                 caller_owned_grads=(gparams if sink is not None else ()))
 
         def step(gt, gt_ready=None):
             if gt_ready is not None:   # ground truth uploaded on a side stream
                 torch.cuda.current_stream().wait_event(gt_ready)
             graph.gt.copy_(gt, non_blocking=True)
-            loss = graph.replay()
-            if sink is not None:
-                sink.all_reduce()
-            return loss
+            return graph.replay()
         step.graph = graph
-        step.mode = "cuda-graph replay (one launch per step)" + ("; one NCCL all-reduce of the flat gradient buffer after it" if sink is not None else "")
+        step.mode = "cuda-graph replay (one launch per step)" + overlap.replace("; NCCL", "; inside the graph: NCCL")
         return step
 
     def step(gt, gt_ready=None):
@@ -195,31 +193,50 @@ def make_step_ours(w, world, lambda_t_smooth=0.0, use_graph=False):
             sink.wait()
         return loss
     step.graph = None
-    step.mode = "kernel by kernel" + ("; gradient all-reduce overlapped with the per-Gaussian backward" if sink is not None else "")
+    step.mode = "kernel by kernel" + overlap
     return step
 
 
-def make_step_subframe_sharded(w, world):
+def make_step_subframe_sharded(w, world, use_graph=False):
     """One blurry view, its sub-frames sharded over the ranks (deblurgs_b200.dist.render_blurry_sharded): partial
     blurred images summed by an all-reduce, every rank evaluates the same L1 loss; the Gaussian gradients are summed
     through the gradient sink (all-reduce of finished rows under the rest of the backward), the trajectory gradients
-    by one small all-reduce."""
+    by one small all-reduce.  Graph mode: all of it -- collectives included -- is one CUDA-graph replay."""
     from deblurgs_b200 import dist as dd
     from deblurgs_b200.loss import blur_photometric_loss
     cmm, g = w["cmm"], w["gaussians"]
     sink = dd.FlatGradBuffer.for_gaussians(g)
+    if os.environ.get("DGS_SINK_RANGES"):
+        sink.n_ranges = int(os.environ["DGS_SINK_RANGES"])
     g.grad_sink = sink
-    cflat = flat_grad_views(cmm.parameters())
+    cbuf = dd.FlatGradBuffer(cmm.parameters())       # trajectory gradients: views of one flat buffer
+
+    def finish():
+        sink.wait()
+        cbuf.all_reduce()
+
+    if use_graph:
+        from deblurgs_b200.graph import BlurryViewGraph
+
+        def render(_graph):
+            blurred, pkg, _ = dd.render_blurry_sharded(cmm, 0, w["bg"])
+            return blurred, pkg["render"], pkg
+        graph = BlurryViewGraph(cmm, 0, w["bg"], (3, w["H"], w["W"]), 0.0, pre_backward=cbuf.zero, post_backward=finish,
+                                caller_owned_grads=g.parameters() + cmm.parameters(), render_fn=render)
+
+        def step(gt, gt_ready=None):
+            graph.gt.copy_(gt, non_blocking=True)
+            return graph.replay()
+        step.graph = graph
+        step.mode = "cuda-graph replay (one launch per step; the image / gradient all-reduces are nodes of the graph)"
+        return step
 
     def step(gt, gt_ready=None):
-        cflat.zero_()
+        cbuf.zero()
         blurred, pkg, _ = dd.render_blurry_sharded(cmm, 0, w["bg"])
         loss = blur_photometric_loss(blurred, pkg["render"], gt, 0.0)
         loss.backward()
-        sink.wait()
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(cflat)
+        finish()
         return loss
     step.graph = None
     step.mode = "kernel by kernel"
@@ -405,7 +422,10 @@ def other_config(name, rank, world, device, steps=3, warmup=3):
     if name == "c1":      # BASELINE config 1 (the CPU-runnable case): launch-bound kernel by kernel, so replayed as a graph
         step = make_step_ours(w, 1, 0.0, True)
     else:
-        step = make_step_subframe_sharded(w, world) if (strong and world > 1) else make_step_ours(w, 1 if strong else world)
+        # graph replay everywhere (DGS_BENCH_EAGER_OTHERS=1: kernel by kernel, for comparison)
+        gmode = os.environ.get("DGS_BENCH_EAGER_OTHERS") != "1"
+        step = (make_step_subframe_sharded(w, world, gmode) if (strong and world > 1)
+                else make_step_ours(w, 1 if strong else world, 0.0, gmode))
     mode = ("subframes-sharded-%d (NCCL all-reduce of the blurred image; gradient all-reduce overlapped with the backward)"
             % world) if (strong and world > 1) else None
     gt = w["gt_host"].to(device)
@@ -461,12 +481,12 @@ def main():
     w = build_workload(args.config, 0 if sharded else rank, device)
     F = w["F"]
     lam = 1e-3 if args.loss == "smooth" else 0.0
-    use_graph = args.impl == "ours" and not args.no_graph and not sharded
+    use_graph = args.impl == "ours" and not args.no_graph
 
     if args.impl == "ours":
         from deblurgs_b200 import _lib
         lib = _lib.load()
-        step = make_step_subframe_sharded(w, eff_world) if sharded else make_step_ours(w, eff_world, lam, use_graph)
+        step = make_step_subframe_sharded(w, eff_world, use_graph) if sharded else make_step_ours(w, eff_world, lam, use_graph)
     else:
         lib = None
         if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "diff_gaussian_rasterization")):
@@ -512,7 +532,9 @@ def main():
             gt_ready = copy_stream.record_event()
         loss = step(gt, gt_ready)
         loss_host = loss.item()
-        if getattr(step, "graph", None) is not None and step.graph.check():   # capacity exceeded: re-captured + replayed
+        # capacity exceeded: re-captured + replayed (with collectives inside the graph the check is itself a collective:
+        # done once after the loop instead; the scene does not change here)
+        if getattr(step, "graph", None) is not None and eff_world == 1 and step.graph.check():
             loss_host = step.graph.loss.item()
         t_now = time.perf_counter()
         step_wall.append((t_now - t_prev) * 1e3)

@@ -19,6 +19,25 @@ def world():
     return 0, 1
 
 
+_DIRECT = {}      # device index -> nccl_direct.DirectComm (or None once creation failed)
+
+
+def direct_comm(device):
+    """The process's direct NCCL communicator for the hot-path collectives (see nccl_direct.py), or None when the
+    default group is not NCCL on a CUDA device (gloo CPU tests, single process).  Created on first use -- a collective
+    call: every rank must reach it, and not from inside a stream capture."""
+    device = torch.device(device)
+    if device.type != "cuda" or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return None
+    if dist.get_backend() != "nccl":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _DIRECT:
+        from .nccl_direct import DirectComm
+        _DIRECT[key] = DirectComm(torch.device("cuda", key))
+    return _DIRECT[key]
+
+
 def subframe_shard(num_subframes, rank, world_size):
     """Contiguous block [start, stop) of sub-frames for `rank`; blocks differ by at most one sub-frame
     and keep temporal neighbours on the same rank (except at block edges)."""
@@ -35,7 +54,11 @@ class _AllReduceSum(torch.autograd.Function):
     def forward(ctx, x):
         y = x.contiguous().clone()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(y, op=dist.ReduceOp.SUM)
+            comm = direct_comm(y.device) if y.dtype == torch.float32 else None
+            if comm is not None:
+                comm.all_reduce_(y)                 # on the current stream: capturable
+            else:
+                dist.all_reduce(y, op=dist.ReduceOp.SUM)
         return y
 
     @staticmethod
@@ -70,6 +93,12 @@ class FlatGradBuffer:
             self.spans[key] = (off, off + p.numel())
             off += p.numel()
         self.works, self.big, self.small_span = [], None, None
+        # NCCL on a CUDA device: the collectives are issued directly on a side stream (fork / join with events), which
+        # also works inside a stream capture; otherwise through torch.distributed (gloo in the CPU tests)
+        self.comm = direct_comm(self.flat.device)
+        self.comm_stream = torch.cuda.Stream(self.flat.device) if self.comm is not None else None
+        self._forked = False
+        self.n_ranges = 4          # row ranges the backward finishes one after the other (each followed by its all-reduce)
 
     @classmethod
     def for_gaussians(cls, g):
@@ -90,26 +119,48 @@ class FlatGradBuffer:
 
     def all_reduce(self):
         if self._active():
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if self.comm is not None:
+                self.comm.all_reduce_(self.flat)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         return self.flat
 
     # ---- sink protocol (called from the backward of rasterizer._RenderStoreBlurry) --------------------
     def begin(self):
         self.works = []
 
+    def _async_all_reduce(self, t):
+        if self.comm is not None:
+            # fork: the side stream picks up behind everything enqueued so far; the caller's stream goes on
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            self.comm.all_reduce_(t, stream=self.comm_stream)
+            self._forked = True
+        else:
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
     def rows_done(self, g0, g1):
-        """Rows [g0, g1) of every Gaussian gradient are final: reduce the big tensor's rows now (asynchronously: the
-        collective runs on NCCL's stream behind everything enqueued so far, the caller's stream goes on)."""
-        if self._active() and self.big is not None and g1 > g0:
-            self.works.append(dist.all_reduce(self.views[self.big][g0:g1], op=dist.ReduceOp.SUM, async_op=True))
+        """Rows [g0, g1) of every Gaussian gradient are final: reduce them now (asynchronously: the collective runs on a
+        side stream behind everything enqueued so far, the caller's stream goes on).  Direct NCCL: the rows of all six
+        tensors as one grouped launch; torch.distributed: the big tensor's rows (the small tensors follow in finish())."""
+        if not (self._active() and self.big is not None and g1 > g0):
+            return
+        if self.comm is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.flat.device))     # fork
+            self.comm.all_reduce_group_([v[g0:g1] for v in self.views.values()], stream=self.comm_stream)
+            self._forked = True
+        else:
+            self._async_all_reduce(self.views[self.big][g0:g1])
 
     def finish(self):
-        if self._active() and self.small_span is not None:
+        if self._active() and self.small_span is not None and self.comm is None:
             a, b = self.small_span
-            self.works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, async_op=True))
+            self._async_all_reduce(self.flat[a:b])
 
     def wait(self):
         """The current stream waits for every collective started since begin()."""
+        if self._forked:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)     # join
+            self._forked = False
         for w in self.works:
             w.wait()
         self.works = []

@@ -29,7 +29,7 @@ class BlurryViewGraph:
     `parameters` (default: the Gaussians' and the trajectory's) get their .grad from the captured backward."""
 
     def __init__(self, cmm, cam_idx, background, gt_shape, lambda_t_smooth=0.0, parameters=None, pre_backward=None,
-                 caller_owned_grads=(), capacity_margin=1.25, post_backward=None):
+                 caller_owned_grads=(), capacity_margin=1.25, post_backward=None, render_fn=None):
         self.cmm, self.cam_idx, self.bg, self.lam = cmm, cam_idx, background, float(lambda_t_smooth)
         dev = cmm.gaussians.get_xyz.device
         self.device = dev
@@ -38,6 +38,10 @@ class BlurryViewGraph:
         # are the .grad of `caller_owned_grads`: those accumulate in place; every other .grad is produced by the graph)
         self.pre_backward = pre_backward
         self.post_backward = post_backward        # captured behind the backward (e.g. a gradient sink's wait())
+        # render_fn(graph) -> (blurred [3,H,W], subframes [F',3,H,W], batched package): replaces cmm.query, e.g. the
+        # sub-frame-sharded render of dist.render_blurry_sharded (its NCCL all-reduce is captured with the rest)
+        self.render_fn = render_fn
+        self.collective = post_backward is not None or render_fn is not None    # may hold NCCL nodes: see check()
         self.owned = set(id(p) for p in caller_owned_grads)
         self.margin = float(capacity_margin)
         self.gt = torch.zeros(gt_shape, dtype=torch.float32, device=dev)
@@ -50,7 +54,11 @@ class BlurryViewGraph:
     def _run(self):
         if self.pre_backward is not None:
             self.pre_backward()
-        out = self.cmm.query(self.cam_idx, "all", background=self.bg)
+        if self.render_fn is not None:
+            blurred, subframes, pkg = self.render_fn(self)
+            out = {"blurred": blurred, "subframes": subframes, "batched": pkg}
+        else:
+            out = self.cmm.query(self.cam_idx, "all", background=self.bg)
         loss = blur_photometric_loss(out["blurred"], out["subframes"], self.gt, self.lam)
         loss.backward()
         if self.post_backward is not None:
@@ -78,7 +86,7 @@ class BlurryViewGraph:
             if capacity is None:
                 pkg = out["batched"]
                 F, P = pkg["radii"].shape
-                H, W = pkg["blurred"].shape[1:]
+                H, W = pkg["render"].shape[2:]
                 hint = rz._CAPACITY_HINT.get((self.device.index, P, F, H, W), 0)
                 capacity = max(int(hint * self.margin / 1.25), 65536)
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -117,9 +125,16 @@ class BlurryViewGraph:
         """Call after synchronising on the replay (e.g. after loss.item()).  False: all good.  True: the scene had
         outgrown the binning capacity; the step was re-captured with a larger one and replayed (synchronously), so
         loss / gradients are now complete."""
-        if int(self.status_host[4]) == 0:
+        over, need = int(self.status_host[4]) != 0, self.num_rendered()
+        if self.collective:
+            # the graph contains collectives: capture (and its eager warm-up) must happen on every rank or on none
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                t = torch.tensor([int(over), need if over else 0], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                over, need = bool(t[0].item()), max(need, int(t[1].item()))
+        if not over:
             return False
-        need = self.num_rendered()
         self._capture(int(need * self.margin) + 65536)
         self.recaptures += 1
         self.graph.replay()

@@ -114,7 +114,8 @@ def render_blurry(world_view_transforms, full_proj_transforms, camera_centers, r
         color, depth, radii, blurred = render_store_blurry(
             pc._xyz, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation, pc._opacity, screenspace_points,
             world_view_transforms, full_proj_transforms, camera_centers, raster_settings, blur_denominator, stats,
-            getattr(pc, "scale_lower_bound", 0.0), getattr(pc, "use_isotropic", False), sink)
+            getattr(pc, "scale_lower_bound", 0.0), getattr(pc, "use_isotropic", False), sink,
+            int(getattr(sink, "n_ranges", 4)))
         return {"render": color, "depth": depth, "blurred": blurred, "viewspace_points": screenspace_points,
                 "visibility_filter": radii > 0, "radii": radii, "densification": stats}
     if hasattr(pc, "get_activated"):

@@ -67,7 +67,26 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     b2, l2, g2, s2 = run(True, use_sink=True)
+
+    # the bench's steps, kernel by kernel vs as ONE CUDA-graph replay with the NCCL collectives as graph nodes
+    # (deblurgs_b200.nccl_direct): same loss, same gradients
+    def bench_step(make, graph_mode):
+        step = make(graph_mode)
+        for _ in range(2):
+            loss = step(gt)
+        torch.cuda.synchronize()
+        return loss.detach().clone(), [p.grad.detach().clone() for p in params]
+    graph_report = []
+    for name, make in (("subframes", lambda gm: bench.make_step_subframe_sharded(w, world, gm)),
+                       ("views", lambda gm: bench.make_step_ours(w, world, 0.0, gm))):
+        le, ge = bench_step(make, False)
+        lg, gg = bench_step(make, True)
+        relg = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item() for a, b in zip(gg, ge))
+        assert abs(lg.item() - le.item()) <= 1e-6 * max(1.0, abs(le.item())) and relg <= 1e-3, (name, lg.item(), le.item(), relg)
+        graph_report.append("%s %.1e" % (name, relg))
+    g.grad_sink = None
     if rank == 0:
+        print("graph replay with in-graph collectives vs kernel by kernel, max gradient rel diff: " + ", ".join(graph_report))
         # the overlapped (gradient sink) path gives the plain path's gradients
         rel_sink = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item() for a, b in zip(g2, g1))
         assert (b2 - b1).abs().max().item() <= 1e-6 and rel_sink <= 1e-3, rel_sink
