@@ -9,7 +9,9 @@
 // gathered once into Morton order (coalesced float4), boxes hold 256 points instead of 1024
 // (tighter AABBs), and a block of 256 Morton-consecutive queries walks the boxes together:
 // a box is staged in shared memory once per block and only when some query of the block
-// cannot reject it, instead of every thread re-reading every accepted box from global memory.
+// cannot reject it, instead of every thread re-reading every accepted box from global memory;
+// runs of 32 boxes are rejected as a whole through a coarse AABB level (the reference tests every
+// box for every point: O(P * P / 1024)).
 #include "dgs_b200.h"
 #include "dgs_internal.cuh"
 #include <cfloat>
@@ -17,9 +19,10 @@
 namespace dgs {
 
 #define KNN_BOX 256
+#define KNN_SUPER 32      // boxes per super-box (the coarse level of the search's pruning)
 
 struct KnnLayout {
-    size_t bbox, codes, keys_a, keys_b, vals_a, idx_sorted, pts, boxes, sort_scratch, ticket, total;
+    size_t bbox, codes, keys_a, keys_b, vals_a, idx_sorted, pts, boxes, supers, sort_scratch, ticket, total;
     size_t stride;   // P rounded up to the sort's chunk
 };
 static KnnLayout knn_layout(size_t P)
@@ -37,6 +40,7 @@ static KnnLayout knn_layout(size_t P)
     L.idx_sorted = o; o = align_up(o + Pp * sizeof(uint32_t));
     L.pts = o; o = align_up(o + P * sizeof(float4));
     L.boxes = o; o = align_up(o + nb * 2 * sizeof(float4));
+    L.supers = o; o = align_up(o + (nb + KNN_SUPER - 1) / KNN_SUPER * 2 * sizeof(float4));
     L.sort_scratch = o; o = align_up(o + sort_scratch_bytes((uint32_t)(Pp / SORT_CHUNK), 8));
     L.ticket = o; o = align_up(o + sizeof(uint32_t));
     L.total = o + 128;
@@ -156,29 +160,45 @@ __device__ __forceinline__ float box_dist(const float4& mn, const float4& mx, co
     return dx * dx + dy * dy + dz * dz;
 }
 
+// AABB of every run of KNN_SUPER consecutive boxes (one warp per super-box).
+__global__ void __launch_bounds__(32) k_knn_super(int nb, const float4* __restrict__ boxes, float4* __restrict__ supers)
+{
+    const int b = blockIdx.x * KNN_SUPER + threadIdx.x;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (b < nb) {
+        const float4 a = boxes[2 * b], c = boxes[2 * b + 1];
+        mn[0] = a.x; mn[1] = a.y; mn[2] = a.z; mx[0] = c.x; mx[1] = c.y; mx[2] = c.z;
+    }
+    for (int d = 0; d < 3; d++)
+        for (int o = 16; o >= 1; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if (threadIdx.x == 0) {
+        supers[2 * blockIdx.x] = make_float4(mn[0], mn[1], mn[2], 0.f);
+        supers[2 * blockIdx.x + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    }
+}
+
+// A block of 256 Morton-consecutive queries walks the boxes together: its own box first (it almost always contains
+// the neighbours, so the rejection radius is small from the start), then the super-boxes outward in Morton order;
+// a super-box no query of the block can reach is skipped as a whole (one vote), so that a block looks at
+// nb / KNN_SUPER coarse boxes plus the few fine ones around it instead of at all nb (3 M points: 12 k boxes).
 __global__ void __launch_bounds__(KNN_BOX) k_knn_search(int P, const float4* __restrict__ sorted,
                                                        const float4* __restrict__ boxes,
+                                                       const float4* __restrict__ supers,
                                                        float* __restrict__ out)
 {
     __shared__ float4 s_pts[KNN_BOX];
-    const int nb = (P + KNN_BOX - 1) / KNN_BOX;
+    const int nb = (P + KNN_BOX - 1) / KNN_BOX, nsb = (nb + KNN_SUPER - 1) / KNN_SUPER;
     const int i = blockIdx.x * KNN_BOX + threadIdx.x;
     const bool live = i < P;
     const float4 me = live ? sorted[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-    // Own box first (it almost always contains the neighbours), then the others outward in
-    // Morton order so the rejection radius shrinks early.
-    for (int step = 0; step < 2 * nb; step++) {
-        int b;
-        if (step == 0) b = blockIdx.x;
-        else {
-            const int k = (step + 1) >> 1;
-            b = (step & 1) ? (int)blockIdx.x + k : (int)blockIdx.x - k;
-        }
-        if (b < 0 || b >= nb) continue;   // block-uniform
+    auto scan_box = [&](int b) {           // block-uniform b
         bool need = false;
         if (live) need = box_dist(boxes[2 * b], boxes[2 * b + 1], me) <= best[2];
-        if (!__syncthreads_or(need)) continue;
+        if (!__syncthreads_or(need)) return;
         const int j = b * KNN_BOX + threadIdx.x;
         if (j < P) s_pts[threadIdx.x] = sorted[j];
         __syncthreads();
@@ -190,6 +210,23 @@ __global__ void __launch_bounds__(KNN_BOX) k_knn_search(int P, const float4* __r
             }
         }
         __syncthreads();
+    };
+    const int own = blockIdx.x, own_sb = own / KNN_SUPER;
+    scan_box(own);
+    for (int step = 0; step < 2 * nsb; step++) {
+        int sb;
+        if (step == 0) sb = own_sb;
+        else {
+            const int k = (step + 1) >> 1;
+            sb = (step & 1) ? own_sb + k : own_sb - k;
+        }
+        if (sb < 0 || sb >= nsb) continue;   // block-uniform
+        bool reach = false;
+        if (live) reach = box_dist(supers[2 * sb], supers[2 * sb + 1], me) <= best[2];
+        if (!__syncthreads_or(reach)) continue;
+        const int b0 = sb * KNN_SUPER, b1 = min(nb, b0 + KNN_SUPER);
+        for (int b = b0; b < b1; b++)
+            if (b != own) scan_box(b);
     }
     if (live) out[__float_as_uint(me.w)] = (best[0] + best[1] + best[2]) / 3.0f;
 }
@@ -213,6 +250,7 @@ int dgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scra
     uint32_t* idx_sorted = (uint32_t*)(sc + L.idx_sorted);
     float4* pts = (float4*)(sc + L.pts);
     float4* boxes = (float4*)(sc + L.boxes);
+    float4* supers = (float4*)(sc + L.supers);
     const int nb = (P + KNN_BOX - 1) / KNN_BOX;
     k_knn_bbox_init<<<1, 32, 0, st>>>(bbox);
     k_knn_bbox<<<min(1024, (P + 255) / 256), 256, 0, st>>>(P, points, bbox);
@@ -223,7 +261,8 @@ int dgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scra
     sort_uniform_u32(1, (uint32_t)P, (uint32_t)L.stride, codes, (uint32_t*)(sc + L.keys_a), (uint32_t*)(sc + L.vals_a),
                      (uint32_t*)(sc + L.keys_b), idx_sorted, ss, 30, st);
     k_knn_gather_boxes<<<nb, KNN_BOX, 0, st>>>(P, points, idx_sorted, pts, boxes);
-    k_knn_search<<<nb, KNN_BOX, 0, st>>>(P, pts, boxes, mean_dist2);
+    k_knn_super<<<(nb + KNN_SUPER - 1) / KNN_SUPER, 32, 0, st>>>(nb, boxes, supers);
+    k_knn_search<<<nb, KNN_BOX, 0, st>>>(P, pts, boxes, supers, mean_dist2);
     { const cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? DGS_OK : dgs::fail_cuda(e, "dgs_knn_mean_dist2"); }
 }
 

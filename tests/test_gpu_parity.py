@@ -325,14 +325,25 @@ def test_pose_kernel_vs_reference_python_golden(tag):
 
 
 @needs_ref
-@pytest.mark.parametrize("P", [5, 1000, 50_000])
-def test_knn_matches_reference(P):
+@pytest.mark.parametrize("P", [5, 1000, 50_000, 2_000_000])
+def test_knn_matches_reference(P, capsys):
     from deblurgs_b200 import distCUDA2
     g = torch.Generator().manual_seed(P)
     pts = (torch.randn(P, 3, generator=g) * torch.tensor([3.0, 1.0, 0.3])).cuda()
     mine = distCUDA2(pts)
     ref = ref_cuda.knn(pts)
     assert torch.equal(mine, ref)
+    if P >= 1_000_000:      # post-densification scale: both searches timed (the coarse box level keeps ours near-linear)
+        def timed(fn):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(pts); e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+        t_mine, t_ref = timed(distCUDA2), timed(ref_cuda.knn)
+        with capsys.disabled():
+            print("\n  simple-knn at P = %d: library %.1f ms, reference %.1f ms" % (P, t_mine, t_ref))
+        assert t_mine < 2000.0
     if P <= 1000:
         d = torch.cdist(pts.double(), pts.double()) ** 2
         d.fill_diagonal_(float("inf"))
