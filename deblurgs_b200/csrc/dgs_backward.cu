@@ -114,7 +114,7 @@ struct __align__(16) BwdWarpSmem {
     uint32_t idr[2][32];                  // Gaussian index | (list position relative to the step's lowest) << 27
     float2 qw[BWD_QN][BWD_QSTRIDE];       // [queued entry][pixel] -> (w1, w2)
     float4 dpix[32];                      // dL/dpix r,g,b,depth of the warp's 32 pixels
-    uint32_t qid[BWD_QN];                 // Gaussian index of the queued entry
+    uint32_t qid[BWD_QN];                 // Gaussian index (| position bits) of the queued entry
 };
 #define BWD_ID_BITS 27
 #define BWD_ID_MASK ((1u << BWD_ID_BITS) - 1u)
@@ -148,7 +148,7 @@ __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn
     uint32_t id = 0;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (live) {
-        id = sm.qid[e];
+        id = sm.qid[e] & BWD_ID_MASK;
         g0 = __ldg(geo0 + id);
         g1 = __ldg(geo1 + id);
     }
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
         };
         auto enqueue = [&](float w1, float w2, uint32_t idr) {
             sm.qw[qn][lane] = make_float2(w1, w2);
-            sm.qid[qn] = idr & BWD_ID_MASK;              // same value from every lane
+            sm.qid[qn] = idr;                            // same value from every lane; the flush strips the position bits
             if (++qn == BWD_QN) {
                 bwd_flush(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
                 qn = 0;

@@ -3,7 +3,7 @@ library vs the reference extension (baseline/_ref) on the same GPU.  Prints one 
 
   python tests/sweep.py > gpurun_out/sweep.jsonl                                                  # 1 GPU, both arms
   python -m torch.distributed.run --nproc-per-node 8 ... tests/sweep.py > gpurun_out/sweep_n8.jsonl  # N GPUs: this
-      library with one view per rank (gradients all-reduced inside the step); the reference is single-GPU and is
+      library with one view per rank (gradient all-reduces inside the replayed graph); the reference is single-GPU and is
       timed at N = 1 only
 """
 import json
@@ -30,7 +30,7 @@ def main():
             cfg += ",C=3"
         w = bench.build_workload(cfg, rank, dev)
         gt = w["gt_host"].to(dev)
-        step = bench.make_step_ours(w, world, 0.0, use_graph=(world == 1))
+        step = bench.make_step_ours(w, world, 0.0, use_graph=True)
         for _ in range(3):
             step(gt)
         ours = bench.time_steps(step, gt, 5, world, dev)

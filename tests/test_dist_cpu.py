@@ -99,3 +99,21 @@ def test_subframe_shard_balanced():
             sizes = [b - a for a, b in blocks]
             assert sum(sizes) == F and max(sizes) - min(sizes) <= 1
             assert blocks[0][0] == 0 and blocks[-1][1] == F
+
+
+def test_direct_nccl_wrapper_binds_the_library_torch_ships_and_stays_off_without_nccl():
+    """deblurgs_b200.nccl_direct: the libnccl it would call exports every entry point it binds (no GPU needed to load
+    it), and the dispatcher in dist.py keeps to torch.distributed when there is no NCCL process group (CPU / gloo)."""
+    import ctypes
+    import os
+    from deblurgs_b200 import dist as dd, nccl_direct
+    path = nccl_direct._find_library()
+    if os.path.isabs(path) and os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        for name in ("ncclGetUniqueId", "ncclCommInitRank", "ncclAllReduce", "ncclGroupStart", "ncclGroupEnd",
+                     "ncclCommDestroy", "ncclGetErrorString"):
+            assert hasattr(lib, name), name
+    assert dd.direct_comm(torch.device("cpu")) is None
+    assert dd.direct_comm(torch.device("cuda", 0)) is None          # no process group in this process
+    buf = dd.FlatGradBuffer([torch.nn.Parameter(torch.zeros(4, 3))])
+    assert buf.comm is None and buf.comm_stream is None
