@@ -139,7 +139,10 @@ def unitquat_to_rotmat(q):
 
 
 def rotmat_to_unitquat(R):
-    """[N,3,3] -> unit quaternions [N,4] XYZW with w >= 0 (largest-component branch for stability)."""
+    """[N,3,3] -> unit quaternions [N,4] XYZW, as `roma.rotmat_to_unitquat` (scene/motion.py:192, test.py:66) returns
+    them: the row of the largest of (m00, m11, m22, trace) is normalised and its sign is NOT canonicalised, so the
+    leading component of the chosen row is positive and w may be negative near a half turn (q and -q are the same
+    rotation; the sign only decides which representative a curve's control points start from)."""
     m = R
     t = m[:, 0, 0] + m[:, 1, 1] + m[:, 2, 2]
     cand = torch.stack([
@@ -152,8 +155,7 @@ def rotmat_to_unitquat(R):
         torch.stack([m[:, 2, 1] - m[:, 1, 2], m[:, 0, 2] - m[:, 2, 0], m[:, 1, 0] - m[:, 0, 1], 1 + t], -1)], 1)
     best = torch.stack([m[:, 0, 0], m[:, 1, 1], m[:, 2, 2], t], -1).argmax(-1)
     q = cand[torch.arange(R.shape[0], device=R.device), best]
-    q = q / q.norm(dim=-1, keepdim=True)
-    return torch.where(q[:, 3:4] < 0, -q, q)
+    return q / q.norm(dim=-1, keepdim=True)
 
 
 def c2w_to_minicam_tensors(rots, transes, projection_matrix_t):

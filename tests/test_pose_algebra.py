@@ -64,7 +64,12 @@ def test_quaternion_convention_is_xyzw_and_round_trips():
     R = pose.unitquat_to_rotmat(q)
     assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.float64)).abs().max().item() < 1e-14
     assert (torch.det(R) - 1).abs().max().item() < 1e-14
-    assert (pose.rotmat_to_unitquat(R) - q).abs().max().item() < 1e-12
+    back = pose.rotmat_to_unitquat(R)
+    # the sign is that of the branch taken (largest of m00, m11, m22, trace), like roma / SciPy: q or -q
+    sign = torch.sign((back * q).sum(-1, keepdim=True))
+    assert (back - sign * q).abs().max().item() < 1e-12
+    big = q.abs().argmax(-1)
+    assert (back[torch.arange(256), big] > 0).all()
     # every branch of the matrix -> quaternion conversion (largest of the three diagonal entries / the trace)
     for axis in range(3):
         v = torch.zeros(1, 4, dtype=torch.float64)
@@ -84,8 +89,7 @@ def test_quaternion_conversions_match_scipy_rotation():
     R_sp = torch.from_numpy(Rot.from_quat(q.numpy()).as_matrix())
     assert (pose.unitquat_to_rotmat(q) - R_sp).abs().max().item() < 1e-14
     mine = pose.rotmat_to_unitquat(R_sp)
-    theirs = torch.from_numpy(Rot.from_matrix(R_sp.numpy()).as_quat())
-    theirs = torch.where(theirs[:, 3:4] < 0, -theirs, theirs)
+    theirs = torch.from_numpy(Rot.from_matrix(R_sp.numpy()).as_quat())     # sign included (no canonicalisation)
     assert (mine - theirs).abs().max().item() < 1e-12
     # near-pi rotations exercise the three non-trace branches
     axes = torch.nn.functional.normalize(torch.randn(64, 3, generator=g, dtype=torch.float64), dim=-1)
@@ -93,8 +97,7 @@ def test_quaternion_conversions_match_scipy_rotation():
     R_pi = torch.from_numpy(Rot.from_rotvec((axes * ang).numpy()).as_matrix())
     mine = pose.rotmat_to_unitquat(R_pi)
     theirs = torch.from_numpy(Rot.from_matrix(R_pi.numpy()).as_quat())
-    sign = torch.sign((mine * theirs).sum(-1, keepdim=True))
-    assert (mine - sign * theirs).abs().max().item() < 1e-9
+    assert (mine - theirs).abs().max().item() < 1e-9
 
 
 class _RefCam:
