@@ -114,7 +114,6 @@ struct __align__(16) BwdWarpSmem {
     uint32_t idr[2][32];                  // Gaussian index | (list position relative to the step's lowest) << 27
     float2 qw[BWD_QN][BWD_QSTRIDE];       // [queued entry][pixel] -> (w1, w2)
     float4 dpix[32];                      // dL/dpix r,g,b,depth of the warp's 32 pixels
-    uint32_t qid[BWD_QN];                 // Gaussian index (| position bits) of the queued entry
 };
 #define BWD_ID_BITS 27
 #define BWD_ID_MASK ((1u << BWD_ID_BITS) - 1u)
@@ -137,7 +136,7 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
 // Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
 // until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the gather
 // fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
-__device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn, float wx0f, float wy0f,
+__device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn, uint32_t myqid, float wx0f, float wy0f,
                                             float ddelx_dx, float ddely_dy, const float4* __restrict__ geo0,
                                             const float4* __restrict__ geo1, float4* __restrict__ gp0,
                                             float4* __restrict__ gp1, float4* __restrict__ gp2)
@@ -145,10 +144,11 @@ __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn
     __syncwarp();
     const unsigned e = lane & 7u, quarter = lane >> 3;
     const bool live = (int)e < qn;
-    uint32_t id = 0;
+    // Gaussian index of queued entry e: lane e kept it in a register when the entry was queued (a shared-memory
+    // array costs one store wavefront per entry, and this kernel is bound by the L1 / shared-memory data pipe)
+    const uint32_t id = __shfl_sync(FULL_MASK, myqid, e) & BWD_ID_MASK;
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
     if (live) {
-        id = sm.qid[e] & BWD_ID_MASK;
         g0 = __ldg(geo0 + id);
         g1 = __ldg(geo1 + id);
     }
@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
     int n_cur = issue_gather(0, wmb, idn);
     load_step(1, wmb, idn);
     int qn = 0;   // queued entries (warp-uniform)
+    uint32_t myqid = 0;   // lane q: id of queued entry q
     for (int k = 0; k < steps; k++, rel += 32) {
         const int n_next = issue_gather((k + 1) & 1, wmb, idn);    // (past the end: no copies, an empty group)
         load_step(k + 2, wmb, idn);
@@ -323,9 +324,9 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
         };
         auto enqueue = [&](float w1, float w2, uint32_t idr) {
             sm.qw[qn][lane] = make_float2(w1, w2);
-            sm.qid[qn] = idr;                            // same value from every lane; the flush strips the position bits
+            if ((int)lane == qn) myqid = idr;            // lane qn remembers the entry's id; the flush strips the position bits
             if (++qn == BWD_QN) {
-                bwd_flush(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+                bwd_flush(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
                 qn = 0;
             }
         };
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
         n_cur = n_next;
     }
     cp_async_wait<0>();
-    if (qn > 0) bwd_flush(sm, lane, qn, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+    if (qn > 0) bwd_flush(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
