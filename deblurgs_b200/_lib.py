@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgs_b200.so")
+# DGS_B200_LIB: another build of the same library (A/B measurements of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("DGS_B200_LIB") or os.path.join(_HERE, "libdgs_b200.so")
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 

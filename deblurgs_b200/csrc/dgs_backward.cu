@@ -136,6 +136,7 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
 // Gaussian's centre afterwards: the entry's own data (centre, conic, opacity) is therefore not needed
 // until after the loop, so it is simply re-read from the geometry records (an L1/L2 hit: the gather
 // fetched it moments ago) while the loop runs, instead of being copied into the queue by phase 1.
+template <bool DEPTH>
 __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn, uint32_t myqid, float wx0f, float wy0f,
                                             float ddelx_dx, float ddely_dy, const float4* __restrict__ geo0,
                                             const float4* __restrict__ geo1, float4* __restrict__ gp0,
@@ -156,12 +157,19 @@ __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn
 #pragma unroll
     for (int pp = 0; pp < 8; pp++) {
         const float2 w = sm.qw[e][quarter * 8 + pp];
-        const float4 dp = sm.dpix[quarter * 8 + pp];
         const float px = (float)pp;
         M0 += w.x;
         Mx = fmaf(w.x, px, Mx);
         Mxx = fmaf(w.x, px * px, Mxx);
-        Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
+        if (DEPTH) {
+            const float4 dp = sm.dpix[quarter * 8 + pp];
+            Cr = fmaf(w.y, dp.x, Cr); Cg = fmaf(w.y, dp.y, Cg); Cb = fmaf(w.y, dp.z, Cb); Cd = fmaf(w.y, dp.w, Cd);
+        } else {
+            // no depth gradient: 12 of the 16 bytes (an 8-byte + a 4-byte load: 3 shared-memory wavefronts instead of 4)
+            const float* dp = reinterpret_cast<const float*>(&sm.dpix[quarter * 8 + pp]);
+            const float2 rg = *reinterpret_cast<const float2*>(dp);
+            Cr = fmaf(w.y, rg.x, Cr); Cg = fmaf(w.y, rg.y, Cg); Cb = fmaf(w.y, dp[2], Cb);
+        }
     }
     const float bx = g0.x - wx0f, by = g0.y - (wy0f + (float)quarter);
     float S0 = M0;
@@ -176,7 +184,8 @@ __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn
         Sy += __shfl_xor_sync(FULL_MASK, Sy, d);   Sxx += __shfl_xor_sync(FULL_MASK, Sxx, d);
         Sxy += __shfl_xor_sync(FULL_MASK, Sxy, d); Syy += __shfl_xor_sync(FULL_MASK, Syy, d);
         Cr += __shfl_xor_sync(FULL_MASK, Cr, d);   Cg += __shfl_xor_sync(FULL_MASK, Cg, d);
-        Cb += __shfl_xor_sync(FULL_MASK, Cb, d);   Cd += __shfl_xor_sync(FULL_MASK, Cd, d);
+        Cb += __shfl_xor_sync(FULL_MASK, Cb, d);
+        if (DEPTH) Cd += __shfl_xor_sync(FULL_MASK, Cd, d);
     }
     if (quarter == 0 && live) {
         const float A = g1.x, B = g1.y, Cc = g1.z, o = g1.w;
@@ -188,6 +197,11 @@ __device__ __forceinline__ void bwd_flush(BwdWarpSmem& sm, unsigned lane, int qn
     __syncwarp();
 }
 
+// DEPTH: a gradient of the depth image is supplied.  Without one (the photometric losses of train.py) the depth
+// of an entry is not read, its record costs 5 instead of 6 shared-memory wavefronts per replay, and the flush
+// skips the fourth dL/dpix component -- this kernel is bound by the L1 / shared-memory data pipe (ncu:
+// l1tex__data_pipe_lsu_wavefronts at 95 % of peak), so wavefronts, not instructions, are what it pays for.
+template <bool DEPTH>
 __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
             const float* d = p.dL_dpix + (size_t)s * 3 * HW;
             dpix0 = d[pix_id]; dpix1 = d[HW + pix_id]; dpix2 = d[2 * HW + pix_id];
         }
-        if (p.dL_dpixdepth) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
+        if (DEPTH) dpixd = p.dL_dpixdepth[(size_t)s * HW + pix_id];
         if (p.dL_dblur) {   // backward of blurred = sum_s color_s / denominator
             dpix0 += p.dL_dblur[pix_id] / p.blur_denominator;
             dpix1 += p.dL_dblur[HW + pix_id] / p.blur_denominator;
@@ -295,8 +309,8 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
         // contribute carries G = alpha = 0 through the same arithmetic (1 / (1 - 0) = 1: T, R unchanged, w1 = w2 = 0).
         // Two entries per iteration: their loads, exponents and colour dot products are independent and overlap; only
         // the T / R recurrences are sequential.
-        auto weigh = [&](uint32_t idr, const float4& g0, const float4& con_o, float& G, float& alpha) {
-            const float dx = g0.x - pixfx, dy = g0.y - pixfy;
+        auto weigh = [&](uint32_t idr, const float2& xy, const float4& con_o, float& G, float& alpha) {
+            const float dx = xy.x - pixfx, dy = xy.y - pixfy;
             // Exponent and exp() are the forward's (= the reference's), operation for operation: the replay must
             // classify every pair exactly as the forward did.  One pair whose alpha falls on the other side of 1/255
             // injects a bogus w * (c . dL/dpix) into R and moves dL/dalpha of EVERY entry in front of it at that pixel
@@ -326,20 +340,36 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
             sm.qw[qn][lane] = make_float2(w1, w2);
             if ((int)lane == qn) myqid = idr;            // lane qn remembers the entry's id; the flush strips the position bits
             if (++qn == BWD_QN) {
-                bwd_flush(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+                bwd_flush<DEPTH>(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
                 qn = 0;
             }
+        };
+        // centre (+ depth when its gradient is wanted) of the entry whose record starts at byte OFF
+        auto cdot_of = [&](const float4& c, float depth) {
+            float d = c.x * dpix0 + c.y * dpix1 + c.z * dpix2;
+            if (DEPTH) d += depth * dpixd;
+            return d;
         };
         int j = 0;
         for (; j + 2 <= n_cur; j += 2, rb += 96u, ib += 8u) {
             const uint32_t idrA = lds_u32(ib), idrB = lds_u32(ib + 4u);
-            const float4 g0A = lds_f4_off<0>(rb), conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
-            const float4 g0B = lds_f4_off<48>(rb), conB = lds_f4_off<64>(rb), cB = lds_f4_off<80>(rb);
+            float2 xyA, xyB;
+            float zA = 0.f, zB = 0.f;
+            if (DEPTH) {
+                const float4 g0A = lds_f4_off<0>(rb), g0B = lds_f4_off<48>(rb);
+                xyA = make_float2(g0A.x, g0A.y); zA = g0A.z;
+                xyB = make_float2(g0B.x, g0B.y); zB = g0B.z;
+            } else {
+                xyA = lds_f2_off<0>(rb);
+                xyB = lds_f2_off<48>(rb);
+            }
+            const float4 conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
+            const float4 conB = lds_f4_off<64>(rb), cB = lds_f4_off<80>(rb);
             float GA, aA, GB, aB;
-            weigh(idrA, g0A, conA, GA, aA);
-            weigh(idrB, g0B, conB, GB, aB);
-            const float cdotA = cA.x * dpix0 + cA.y * dpix1 + cA.z * dpix2 + g0A.z * dpixd;
-            const float cdotB = cB.x * dpix0 + cB.y * dpix1 + cB.z * dpix2 + g0B.z * dpixd;
+            weigh(idrA, xyA, conA, GA, aA);
+            weigh(idrB, xyB, conB, GB, aB);
+            const float cdotA = cdot_of(cA, zA);
+            const float cdotB = cdot_of(cB, zB);
             float w1A, w2A, w1B, w2B;
             replay(GA, aA, conA.w, cdotA, w1A, w2A);
             replay(GB, aB, conB.w, cdotB, w1B, w2B);
@@ -348,18 +378,25 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
         }
         if (j < n_cur) {
             const uint32_t idrA = lds_u32(ib);
-            const float4 g0A = lds_f4_off<0>(rb), conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
+            float2 xyA;
+            float zA = 0.f;
+            if (DEPTH) {
+                const float4 g0A = lds_f4_off<0>(rb);
+                xyA = make_float2(g0A.x, g0A.y); zA = g0A.z;
+            } else {
+                xyA = lds_f2_off<0>(rb);
+            }
+            const float4 conA = lds_f4_off<16>(rb), cA = lds_f4_off<32>(rb);
             float GA, aA, w1A, w2A;
-            weigh(idrA, g0A, conA, GA, aA);
-            const float cdotA = cA.x * dpix0 + cA.y * dpix1 + cA.z * dpix2 + g0A.z * dpixd;
-            replay(GA, aA, conA.w, cdotA, w1A, w2A);
+            weigh(idrA, xyA, conA, GA, aA);
+            replay(GA, aA, conA.w, cdot_of(cA, zA), w1A, w2A);
             enqueue(w1A, w2A, idrA);
         }
         __syncwarp();      // every lane is done with this buffer before step k+2 is gathered into it
         n_cur = n_next;
     }
     cp_async_wait<0>();
-    if (qn > 0) bwd_flush(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
+    if (qn > 0) bwd_flush<DEPTH>(sm, lane, qn, myqid, rx0, ry0, ddelx_dx, ddely_dy, geo0, geo1, gp0, gp1, gp2);
 }
 
 void launch_render_bwd(const BwdParams& p, cudaStream_t st)
@@ -368,7 +405,8 @@ void launch_render_bwd(const BwdParams& p, cudaStream_t st)
     if (f.F == 0 || f.W == 0 || f.H == 0) return;
     static_assert(sizeof(BwdWarpSmem) * BWD_WARPS <= 48 * 1024, "fits the default dynamic shared-memory limit: no per-device opt-in needed");
     dim3 grid(f.tiles_x, f.tiles_y * (8 / BWD_WARPS), f.F), block(BWD_THREADS);
-    k_render_bwd<<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
+    if (p.dL_dpixdepth != nullptr) k_render_bwd<true><<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
+    else k_render_bwd<false><<<grid, block, sizeof(BwdWarpSmem) * BWD_WARPS, st>>>(p);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -109,6 +109,32 @@ def test_depth_key_paths_give_the_reference_order(F, far):
 
 
 @needs_ref
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_backward_without_a_depth_gradient(name):
+    """The blend backward has its own instantiation for "no gradient of the depth image" (the photometric losses:
+    the entry's depth is not read, dL/dpix is three components).  Against the reference with a zero depth gradient,
+    and against this library's own with-depth instantiation fed the same zeros."""
+    cam, scene, bg, view, proj, campos, fw, refs = _compare_forward(name)
+    F, W, H = view.shape[0], cam.width, cam.height
+    g = torch.Generator().manual_seed(11)
+    dpix = (torch.randn(F, 3, H, W, generator=g) / (3 * H * W)).cuda()
+    zeros = torch.zeros(F, 1, H, W).cuda()
+    mine = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix, None)
+    with_zeros = pu.ours_backward(cam, scene, bg, view, proj, campos, fw, dpix, zeros)
+    acc = None
+    for s in range(F):
+        b = ref_cuda.backward(refs[s], scene.means3D, scene.shs, None, scene.scales, scene.rotations, None,
+                              view[s].contiguous(), proj[s].contiguous(), campos[s].contiguous(), bg, W, H,
+                              cam.tanfovx, cam.tanfovy, 3, dpix[s].contiguous(), zeros[s].contiguous())
+        acc = {k: v.double().clone() for k, v in b.items()} if acc is None else {k: acc[k] + v.double() for k, v in b.items()}
+    for k in ["dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"]:
+        assert relmax(mine[k], acc[k]) <= 1e-3, k
+        assert relmax(mine[k], with_zeros[k]) <= 1e-5, k        # same sums; only the order of the float REDs differs
+    for k in ["dL_dviewmatrix", "dL_dprojmatrix", "dL_dmeans2D"]:
+        assert relmax(mine[k], with_zeros[k]) <= 1e-5, k
+
+
+@needs_ref
 @pytest.mark.parametrize("name,sig", [("tiny", False), ("tiny", True), ("small", False), ("c1", False)])
 def test_backward_vs_reference_cuda(name, sig):
     cam, scene, bg, view, proj, campos, fw, refs = _compare_forward(name, use_sigmoid=sig)
