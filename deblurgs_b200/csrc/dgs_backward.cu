@@ -76,7 +76,7 @@ struct HalvingReduce {
 
 // ---------------------------------------------------------------------------------------
 // tile blending, backward.  grid = (tiles_x, tiles_y * 8/BWD_WARPS, F), BWD_THREADS threads = one 16 x 8 strip of a
-// tile; each warp owns an 8x4 pixel rectangle -- the same rectangle as one warp of the forward's tile block -- and
+// tile; each warp owns an 8x4 pixel rectangle -- one half (rows y..y+3 of the 8 columns) of a forward warp's 8x8 block -- and
 // works on its own: there is no block-level barrier in this kernel.
 // gradient scratch = three planes of N float4:
 //   g0: dmean2D(x,y), dconic(x,y) | g1: dconic(w), dopacity, ddepth, - | g2: dcolor(r,g,b), -
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_render_bwd(const BwdParams p)
     const float pixfx = (float)pixx, pixfy = (float)pixy;
 
     const uint2 range = decode_range(p.ranges[(size_t)s * f.tiles_x * f.tiles_y + tile]);
-    const unsigned wbit = strip * BWD_WARPS + warp;      // this warp's index among the 8 warps of the forward's tile block
+    const unsigned wbit = strip * BWD_WARPS + warp;      // this rectangle's bit in the hand-over byte: 2 * (4-row band) + column half
 
     const float T_final = inside ? p.final_T[(size_t)s * HW + pix_id] : 0.f;
     const int last_contributor = inside ? (int)p.n_contrib[(size_t)s * HW + pix_id] : 0;
