@@ -642,9 +642,11 @@ def main():
     dom = max((k for k in stage_ms if k in flops or k in abytes), key=stage_ms.get)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    limiter = None
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.config, {}).get(dom)
+            tj = json.load(f).get(args.config, {})
+        traffic, limiter = tj.get(dom), tj.get("limiters", {}).get(dom)
     hbm, src = measured_peaks()
     if dom in flops:
         ach = flops[dom] / (stage_ms[dom] * 1e-3) / 1e12
@@ -654,6 +656,8 @@ def main():
                                           "lanes x 2; the SM clock sampled during the timed region was %s MHz)"
                                           % (mhz.value, n_sm, clocks["sm_mhz"]),
                            "algorithmic_flops_per_launch": flops[dom], "ms_per_launch": stage_ms[dom]}
+        if limiter:   # what ncu says binds the kernel (recorded from the committed capture, not measured in this run)
+            out["roofline"]["measured_limiter"] = limiter
         if traffic:   # why the bound is not HBM: measured DRAM traffic of the same kernel against the copy bandwidth
             out["roofline"]["dram_gbs"] = traffic / (stage_ms[dom] * 1e-3) / 1e9
             out["roofline"]["dram_frac_of_hbm_peak"] = out["roofline"]["dram_gbs"] / hbm

@@ -54,6 +54,10 @@ WANT = [
     ("dram__bytes_write.sum", "DRAM write"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "global RED sectors"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data-pipe (LSU) wavefronts, % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles active %"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe cycles active %"),
 ]
 STALLS = ["barrier", "wait", "short_scoreboard", "long_scoreboard", "not_selected", "selected", "branch_resolving",
           "math_pipe_throttle", "lg_throttle", "mio_throttle", "dispatch_stall", "no_instruction"]
