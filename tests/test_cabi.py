@@ -189,3 +189,30 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.split() == ["100", "1000", "10", "4", "1"]
+
+
+def test_blend_kernels_are_built_with_the_sm100_instructions_the_design_names():
+    """DESIGN.md section 3 / profiles/r2_ncu_kernels.md: the forward blend runs its per-pixel arithmetic as packed FP32
+    (FFMA2 / FMUL2 / FADD2, sm_100), the backward gathers with cp.async (LDGSTS) and accumulates with 16-byte vector
+    reductions (REDG ... F32x4).  Checked on the SASS of the objects build() produced (no GPU needed)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from deblurgs_b200 import build
+    build.build_library()
+
+    def sass(obj, fun):
+        r = subprocess.run([cuobjdump, "-sass", "-fun", fun, os.path.join(build.OBJ, obj)], capture_output=True, text=True)
+        assert r.returncode == 0 and "Function" in r.stdout, r.stderr[-500:]
+        return r.stdout
+
+    fwd = sass("dgs_forward.o", "_ZN3dgs12k_render_fwdENS_9FwdParamsEPK5uint2PKjPhPfPjS7_S7_")
+    assert "sm_100a" in fwd
+    assert fwd.count("FFMA2") >= 6 and "FMUL2" in fwd and "FADD2" in fwd and "FFMA2.RM" in fwd
+    assert fwd.count("MUFU.EX2") == 2          # one exponential per pixel of the lane's pair, nowhere else
+    for depth in ("0", "1"):
+        bwd = sass("dgs_backward.o", "_ZN3dgs12k_render_bwdILb%sEEEvNS_9BwdParamsE" % depth)
+        assert "LDGSTS.E.128" in bwd and "REDG.E.ADD.F32x4" in bwd
+        assert "BAR.SYNC" not in bwd           # warp-independent: no block-level barrier
