@@ -3,7 +3,9 @@
 //   A: scalar FFMA chains            B: packed FFMA2 chains (same number of FMAs)
 //   C: scalar FFMA + as many LOP3    D: packed FFMA2 + the same LOP3 count (same FMAs as C)
 //   E / F: the same with half as many LOP3 (so that the half-rate ALU pipe is not what binds)
-// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/ffma2_probe.cu -o tools/ffma2_probe
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/ffma2_probe.cu -o build/ffma2_probe   (run it on the GPU box)
+// Measured on a B200 (1965 MHz): A 70.5 TFLOP/s, B 72.8, C 35.5, D 36.1 (the half-rate ALU pipe binds C and D), E 47.0, F 69.4:
+// with issue slots as the limit, the packed form is 1.48x faster for the same arithmetic.
 #include <cstdio>
 #include <cuda_runtime.h>
 
